@@ -1,0 +1,44 @@
+// holo_api.cu -- version / error reporting of libholo_b200 (see include/holo_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "holo_api.cuh"
+
+namespace holo {
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace holo
+
+extern "C" {
+
+int holo_abi_version(void) { return HOLO_ABI_VERSION; }
+
+const char* holo_last_error(void) { return holo::g_err; }
+
+int holo_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        holo::set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int holo_check_launch(const char* who) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        holo::set_error("%s: kernel launch failed: %s", who, cudaGetErrorString(e));
+        return HOLO_ERR_CUDA;
+    }
+    return HOLO_OK;
+}
+
+}  // extern "C"

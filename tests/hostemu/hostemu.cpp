@@ -1,0 +1,196 @@
+// hostemu.cpp -- TEST-ONLY host build of the per-element kernel math in holodeck_b200/csrc/holo_math.cuh.
+//
+// The CUDA kernels are thin parallel wrappers around HOLO_HD inline functions; this file drives
+// the same functions with plain loops so that the arithmetic (not the launch machinery) can be
+// compared against the reference on a machine without a GPU.  It is never loaded by the product
+// (holodeck_b200/_lib.py only ever opens libholo_b200.so) and it is not an oracle: the oracle is
+// oracle/_ref (the compiled reference) plus oracle/*.py|c.
+//
+// build: g++ -O2 -ffp-contract=off -shared -fPIC -o tests/hostemu/libhostemu.so tests/hostemu/hostemu.cpp
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../holodeck_b200/csrc/holo_math.cuh"
+
+using namespace holo;
+
+static CyConsts to_cc(const holo_cy_consts& c) {
+    CyConsts cc;
+    cc.gw_dadt_sep_const = c.gw_dadt_sep_const;
+    cc.kepler_const_freq = c.kepler_const_freq;
+    cc.kepler_const_sepa = c.kepler_const_sepa;
+    cc.four_pi_c_over_mpc = c.four_pi_c_over_mpc;
+    return cc;
+}
+
+extern "C" {
+
+void emu_sam_density(const double* mtot, const double* mrat, const double* redz, const double* age_z,
+                     const double* dtdz_z, int M, int Q, int Z, const holo_sam_params* par,
+                     double* dens, double* gmt_time, double* redz_prime) {
+    for (int ii = 0; ii < M; ++ii)
+        for (int jj = 0; jj < Q; ++jj)
+            for (int kk = 0; kk < Z; ++kk) {
+                int64_t i = ((int64_t)ii * Q + jj) * Z + kk;
+                DensityOut o = density_point(*par, mtot[ii], mrat[jj], redz[kk], age_z[kk], dtdz_z[kk]);
+                dens[i] = o.dens;
+                if (gmt_time) gmt_time[i] = o.gmt_time;
+                if (redz_prime) redz_prime[i] = o.redz_prime;
+            }
+}
+
+struct HostLifetime {
+    const double *sepa, *p1, *p2, *gw;
+    int nsteps;
+    double target;
+    double operator()(double norm_log10) const {
+        double norm = pow(10.0, norm_log10);
+        double part[32];
+        for (int lane = 0; lane < 32; ++lane) {
+            double acc = 0.0;
+            for (int s = lane; s < nsteps; s += 32) {
+                double dl = (-norm * p1[s]) / p2[s] + gw[s];
+                double dr = (-norm * p1[s + 1]) / p2[s + 1] + gw[s + 1];
+                acc += 2.0 * (sepa[s + 1] - sepa[s]) / (dl + dr);
+            }
+            part[lane] = acc;
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            double nxt[32];
+            for (int l = 0; l < 32; ++l) nxt[l] = part[l] + part[l ^ off];
+            memcpy(part, nxt, sizeof(part));
+        }
+        return part[0] - target;
+    }
+};
+
+void emu_norm_2pwl(holo_cy_consts c, double target_time, const double* mtot, const double* mrat, int N,
+                   double sepa_init, double rchar, double gi, double go, int nsteps, int mode,
+                   const double* norm_in, double* out) {
+    CyConsts cc = to_cc(c);
+    int ne = nsteps + 1;
+    std::vector<double> sepa(ne), p1(ne), p2(ne), gw(ne);
+    double sepa_init_log10 = log10(sepa_init);
+    for (int i = 0; i < N; ++i) {
+        double mt = mtot[i], mr = mrat[i];
+        double dx = (sepa_init_log10 - log10(3.0 * CY_SCHW * mt)) / nsteps;
+        double slog = sepa_init_log10;
+        for (int k = 0; k < ne; ++k) {
+            double sp = pow(10.0, slog);
+            double xx = sp / rchar;
+            sepa[k] = sp;
+            p1[k] = pow(1.0 + xx, -go + gi);
+            p2[k] = pow(xx, gi - 1.0);
+            gw[k] = hard_gw(cc, mt, mr, sp);
+            slog -= dx;
+        }
+        HostLifetime fn{sepa.data(), p1.data(), p2.data(), gw.data(), nsteps, mode == 0 ? target_time : 0.0};
+        out[i] = (mode == 0) ? brentq(fn, -20.0, 20.0, 1e-3, 1e-5, 100) : fn(norm_in[i]);
+    }
+}
+
+void emu_dbn_2pwl(holo_cy_consts c, const double* fobs, int F, double sepa_init, int nsteps,
+                  const double* hard_norm, double rchar, double gi, double go, const double* nden,
+                  const double* mtot, const double* mrat, const double* redz, const double* gmt_time,
+                  int M, int Q, int Z, const double* grid_z, const double* grid_dcom,
+                  const double* grid_age, int n_interp, double* redz_final, double* diff_num) {
+    CyConsts cc = to_cc(c);
+    int ne = nsteps + 1;
+    std::vector<double> sepa(ne), dadt(ne), frst(ne), tevo(ne), dt(ne), zage(Z);
+    double sepa_init_log10 = log10(sepa_init);
+    for (int k = 0; k < Z; ++k) {
+        int idx = bracket_decreasing(n_interp, redz[k], grid_z);
+        zage[k] = interp_at_index(idx, redz[k], grid_z, grid_age);
+    }
+    for (int ii = 0; ii < M; ++ii)
+        for (int jj = 0; jj < Q; ++jj) {
+            int mq = ii * Q + jj;
+            double mt = mtot[ii], mr = mrat[jj], norm = hard_norm[mq];
+            double dx = (sepa_init_log10 - log10(3.0 * CY_SCHW * mt)) / nsteps;
+            double slog = sepa_init_log10;
+            for (int k = 0; k < ne; ++k) {
+                double sp = pow(10.0, slog);
+                sepa[k] = sp;
+                dadt[k] = hard_func_2pwl_gw(cc, mt, mr, sp, norm, rchar, gi, go);
+                frst[k] = kepler_freq_from_sepa(cc, mt, sp);
+                slog -= dx;
+            }
+            tevo[0] = 0.0;
+            double te = 0.0;
+            for (int k = 0; k < nsteps; ++k) {
+                dt[k] = 2.0 * (sepa[k + 1] - sepa[k]) / (dadt[k] + dadt[k + 1]);
+                te += dt[k];
+                tevo[k + 1] = te;
+            }
+            Track2pwl t;
+            t.frst = frst.data(); t.tevo = tevo.data(); t.dt = dt.data(); t.nsteps = nsteps;
+            t.tage = grid_age; t.gz = grid_z; t.gdc = grid_dcom; t.n_interp = n_interp;
+            t.age_universe = grid_age[n_interp - 1];
+            for (int kk = 0; kk < Z; ++kk)
+                for (int ff = 0; ff < F; ++ff) {
+                    double rz = -1.0, dn = 0.0;
+                    int64_t b = (int64_t)mq * Z + kk;
+                    dbn_2pwl_cell(cc, t, mt, mr, norm, rchar, gi, go, nden[b], gmt_time[b], zage[kk],
+                                  fobs[ff], &rz, &dn);
+                    redz_final[b * F + ff] = rz;
+                    diff_num[b * F + ff] = dn;
+                }
+        }
+}
+
+void emu_dbn_gw(holo_cy_consts c, const double* fobs, int F, const double* nden, const double* mtot,
+                const double* mrat, const double* redz_prime, int M, int Q, int Z, const double* grid_z,
+                const double* grid_dcom, int n_interp, double* redz_final, double* diff_num) {
+    CyConsts cc = to_cc(c);
+    for (int ii = 0; ii < M; ++ii)
+        for (int jj = 0; jj < Q; ++jj)
+            for (int kk = 0; kk < Z; ++kk)
+                for (int ff = 0; ff < F; ++ff) {
+                    int64_t b = ((int64_t)ii * Q + jj) * Z + kk;
+                    dbn_gw_cell(cc, mtot[ii], mrat[jj], nden[b], redz_prime[b], fobs, ff, grid_z,
+                                grid_dcom, n_interp, &redz_final[b * F + ff], &diff_num[b * F + ff]);
+                }
+}
+
+void emu_integrate_and_strain(const holo_cosmo_params* cosmo, double gw_src_const, double nwtg,
+                              const double* log10_mtot, const double* mrat, const double* redz,
+                              const double* dln_freq, const double* dnum, const double* redz_final,
+                              const double* rz_mid, const double* mt_mid, const double* mr_mid,
+                              const double* fc, const double* fc_over_df, int M, int Q, int Z, int F,
+                              double* numb, double* h2fdf, double* zmid, double* dcom, double* sepa,
+                              double* angs) {
+    GLTable gl;
+    for (int i = 0; i < GL_ORDER; ++i) { gl.x[i] = cosmo->gl_x[i]; gl.w[i] = cosmo->gl_w[i]; }
+    int Mb = M - 1, Qb = Q - 1, Zb = Z - 1;
+    int64_t sZ = F, sQ = (int64_t)Z * F, sM = (int64_t)Q * Z * F;
+    bool want_par = zmid || dcom || sepa || angs;
+    for (int mm = 0; mm < Mb; ++mm)
+        for (int qq = 0; qq < Qb; ++qq) {
+            double mc = chirp_mass_mtmr(mt_mid[mm], mr_mid[qq]);
+            for (int zz = 0; zz < Zb; ++zz)
+                for (int ff = 0; ff < F; ++ff) {
+                    int64_t i = (((int64_t)mm * Qb + qq) * Zb + zz) * F + ff;
+                    int64_t base = mm * sM + qq * sQ + zz * sZ + ff;
+                    if (numb) {
+                        double dm = log10_mtot[mm + 1] - log10_mtot[mm];
+                        double dmdq = dm * (mrat[qq + 1] - mrat[qq]);
+                        double dmdqdz = dmdq * (redz[zz + 1] - redz[zz]);
+                        numb[i] = integrate_bin(dnum, sM, sQ, sZ, base, dmdqdz, dln_freq[ff]);
+                    }
+                    if (h2fdf) {
+                        double zc = redz_final ? corner_mean_redz(redz_final, sM, sQ, sZ, base) : rz_mid[zz];
+                        StrainOut o = strain_cell(gl, cosmo->hubble_distance, cosmo->om0, gw_src_const,
+                                                  nwtg, zc, mc, mt_mid[mm], fc[ff], fc_over_df[ff], want_par);
+                        h2fdf[i] = o.h2fdf;
+                        if (zmid) zmid[i] = o.zmid;
+                        if (dcom) dcom[i] = o.dcom;
+                        if (sepa) sepa[i] = o.sepa;
+                        if (angs) angs[i] = o.angs;
+                    }
+                }
+        }
+}
+
+}  // extern "C"
