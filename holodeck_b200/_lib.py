@@ -136,6 +136,7 @@ SIGNATURES = {
     "holo_abi_version": [],
     "holo_last_error": [],
     "holo_device_count": [],
+    "holo_launch_count": [],
     "holo_sam_density": [_P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(SamParams), _P, _P, _P, _P],
     "holo_zero_stalled": [_P, _P, _L, _P],
     "holo_find_2pwl_hardening_norm": [CyConsts, _D, _P, _P, _I, _D, _D, _D, _D, _I, _P, _P],
@@ -155,7 +156,7 @@ SIGNATURES = {
     "holo_loudest": [C.POINTER(LoudestArgs), _P],
     "holo_ss_bg_hc": [_P, _P, _I, _I, _I, _I, _I, _L, _U, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                       _P, _L, _P],
-    "holo_realize_workspace_bytes": [_L, _I, _I, _I],
+    "holo_realize_workspace_bytes": [_I, _L, _I, _I],
     "holo_poisson_as_needed": [_P, _L, _U, _U, _D, _P, _P],
     "holo_sam_calc_gwb_single_eccen": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I,
                                        _L, _U, _P, _P, _L, _P],
@@ -163,6 +164,7 @@ SIGNATURES = {
 }
 _RESTYPES = {
     "holo_last_error": C.c_char_p,
+    "holo_launch_count": C.c_int64,
     "holo_loudest_workspace_bytes": C.c_int64,
     "holo_realize_workspace_bytes": C.c_int64,
     "holo_eccen_workspace_bytes": C.c_int64,

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "holo_api.cuh"
 
 namespace holo {
@@ -13,9 +15,13 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace holo
 
 extern "C" {
+
+int64_t holo_launch_count(void) { return (int64_t)holo::g_launches.load(); }
 
 int holo_abi_version(void) { return HOLO_ABI_VERSION; }
 

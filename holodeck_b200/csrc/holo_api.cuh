@@ -6,6 +6,7 @@
 
 namespace holo {
 void set_error(const char* fmt, ...);
+void count_launches(int n);
 }
 
 extern "C" int holo_check_launch(const char* who);

@@ -376,14 +376,14 @@ int holo_sam_density(const double* mtot, const double* mrat, const double* redz,
     HOLO_REQUIRE(par->mmb[3] > 0.0, "holo_sam_density: bulge fraction must be > 0");
     int64_t n = (int64_t)M * Q * Z;
     density_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        mtot, mrat, redz, age_z, dtdz_z, M, Q, Z, *par, dens, gmt_time, redz_prime);
+        mtot, mrat, redz, age_z, dtdz_z, M, Q, Z, *par, dens, gmt_time, redz_prime); holo::count_launches(1);
     return holo_check_launch("holo_sam_density");
 }
 
 int holo_zero_stalled(double* dens, const double* redz_prime, int64_t n, void* stream) {
     HOLO_REQUIRE(dens && redz_prime && n >= 0, "holo_zero_stalled: bad argument");
     if (n == 0) return HOLO_OK;
-    zero_stalled_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dens, redz_prime, n);
+    zero_stalled_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dens, redz_prime, n); holo::count_launches(1);
     return holo_check_launch("holo_zero_stalled");
 }
 
@@ -399,7 +399,7 @@ static int launch_norm(holo_cy_consts cc, double target_time, const double* mtot
         HOLO_CUDA(cudaFuncSetAttribute(norm_2pwl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (N + NORM_WARPS - 1) / NORM_WARPS;
     norm_2pwl_kernel<<<blocks, NORM_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        to_cc(cc), target_time, mtot, mrat, N, log10(sepa_init), rchar, gi, go, nsteps, mode, norm_in, out);
+        to_cc(cc), target_time, mtot, mrat, N, log10(sepa_init), rchar, gi, go, nsteps, mode, norm_in, out); holo::count_launches(1);
     return holo_check_launch(who);
 }
 
@@ -426,7 +426,7 @@ int holo_hard_func_2pwl_gw(holo_cy_consts cc, const double* mtot, const double* 
     HOLO_REQUIRE(mtot && mrat && sepa && norm && dadt && N >= 0, "holo_hard_func_2pwl_gw: bad argument");
     if (N == 0) return HOLO_OK;
     hard_func_kernel<<<grid_for(N, 256), 256, 0, (cudaStream_t)stream>>>(
-        to_cc(cc), mtot, mrat, sepa, norm, rchar, gamma_inner, gamma_outer, N, dadt);
+        to_cc(cc), mtot, mrat, sepa, norm, rchar, gamma_inner, gamma_outer, N, dadt); holo::count_launches(1);
     return holo_check_launch("holo_hard_func_2pwl_gw");
 }
 
@@ -446,7 +446,7 @@ int holo_dbn_2pwl(holo_cy_consts cc, const double* fobs_orb, int F, double sepa_
     dbn_2pwl_kernel<<<M * Q, DBN_THREADS, smem, (cudaStream_t)stream>>>(
         to_cc(cc), fobs_orb, F, log10(sepa_init), num_steps, hard_norm, rchar, gamma_inner,
         gamma_outer, nden, mtot, mrat, redz, gmt_time, M, Q, Z, grid_z, grid_dcom, grid_age, n_interp,
-        redz_final, diff_num);
+        redz_final, diff_num); holo::count_launches(1);
     return holo_check_launch("holo_dbn_2pwl");
 }
 
@@ -461,7 +461,7 @@ int holo_dbn_gw(holo_cy_consts cc, const double* fobs_orb, int F, const double* 
     int64_t n = (int64_t)M * Q * Z * F;
     dbn_gw_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
         to_cc(cc), fobs_orb, F, nden, mtot, mrat, redz_prime, M, Q, Z, grid_z, grid_dcom, n_interp,
-        redz_final, diff_num);
+        redz_final, diff_num); holo::count_launches(1);
     return holo_check_launch("holo_dbn_gw");
 }
 
@@ -477,7 +477,7 @@ int holo_integrate_differential_number_3dx1d(const double* log10_mtot, const dou
     GLTable gl{};
     bin_kernel<true, false><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
         g, gl, 0, 0, 0, 0, log10_mtot, mrat, redz, dln_freq, dnum, nullptr, nullptr, nullptr, nullptr,
-        nullptr, nullptr, numb, nullptr, nullptr, nullptr, nullptr, nullptr);
+        nullptr, nullptr, numb, nullptr, nullptr, nullptr, nullptr, nullptr); holo::count_launches(1);
     return holo_check_launch("holo_integrate_differential_number_3dx1d");
 }
 
@@ -492,7 +492,7 @@ static GLTable to_gl(const holo_cosmo_params* c) {
 static int chirp_table(const double* mt_mid, const double* mr_mid, int Mb, int Qb, double** mc,
                        cudaStream_t st) {
     HOLO_CUDA(cudaMallocAsync((void**)mc, sizeof(double) * (size_t)Mb * Qb, st));
-    chirp_table_kernel<<<(Mb * Qb + 255) / 256, 256, 0, st>>>(mt_mid, mr_mid, Mb, Qb, *mc);
+    chirp_table_kernel<<<(Mb * Qb + 255) / 256, 256, 0, st>>>(mt_mid, mr_mid, Mb, Qb, *mc); holo::count_launches(1);
     return holo_check_launch("chirp_table");
 }
 
@@ -513,7 +513,7 @@ int holo_char_strain_sq(const holo_cosmo_params* cosmo, double gw_src_const, dou
     bin_kernel<false, true><<<grid_for(n, 256), 256, 0, st>>>(
         g, to_gl(cosmo), cosmo->hubble_distance, cosmo->om0, gw_src_const, nwtg, nullptr, nullptr,
         nullptr, nullptr, nullptr, redz_final, rz_mid, mc, mt_mid, fc, fc_over_df, nullptr, h2fdf,
-        zmid, dcom, sepa, angs);
+        zmid, dcom, sepa, angs); holo::count_launches(1);
     rc = holo_check_launch("holo_char_strain_sq");
     cudaFreeAsync(mc, st);
     return rc;
@@ -538,7 +538,7 @@ int holo_integrate_and_strain(const holo_cosmo_params* cosmo, double gw_src_cons
     bin_kernel<true, true><<<grid_for(n, 256), 256, 0, st>>>(
         g, to_gl(cosmo), cosmo->hubble_distance, cosmo->om0, gw_src_const, nwtg, log10_mtot, mrat, redz,
         dln_freq, dnum, redz_final, nullptr, mc, mt_mid, fc, fc_over_df, numb, h2fdf, zmid, dcom,
-        sepa, angs);
+        sepa, angs); holo::count_launches(1);
     rc = holo_check_launch("holo_integrate_and_strain");
     cudaFreeAsync(mc, st);
     return rc;
@@ -555,8 +555,8 @@ int holo_gwb_expectation(const double* number, const double* h2fdf, int64_t ncel
     if (nblk < 1) nblk = 1;
     double* partial = nullptr;
     HOLO_CUDA(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)nblk * F, st));
-    expect_partial_kernel<<<nblk, 32 * EXP_ROWS, 0, st>>>(number, h2fdf, ncell, F, cpb, partial);
-    expect_final_kernel<<<(F + 63) / 64, 64, 0, st>>>(partial, nblk, F, hc2);
+    expect_partial_kernel<<<nblk, 32 * EXP_ROWS, 0, st>>>(number, h2fdf, ncell, F, cpb, partial); holo::count_launches(1);
+    expect_final_kernel<<<(F + 63) / 64, 64, 0, st>>>(partial, nblk, F, hc2); holo::count_launches(1);
     int rc = holo_check_launch("holo_gwb_expectation");
     cudaFreeAsync(partial, st);
     return rc;

@@ -1,0 +1,860 @@
+// holo_realize.cu -- K3 (realised GWB) and K4 (loudest-source / background split) for sm_100a.
+//
+// Replaces the reference's sequential loops
+//   _sam_poisson_gwb                         holodeck/cyutils.pyx:862-897
+//   _loudest_hc_from_sorted                  holodeck/cyutils.pyx:1266-1344
+//   _loudest_hc_and_par_from_sorted          holodeck/cyutils.pyx:1409-1538
+//   _loudest_hc_and_par_from_sorted_redz     holodeck/cyutils.pyx:1615-1767
+//   _ss_bg_hc / _ss_bg_hc_and_par            holodeck/cyutils.pyx:935-1178
+//
+// Parallel decomposition (see DESIGN.md section "K3/K4"):
+//   * one THREAD per realization, one CTA per (cell chunk, group of 4 frequencies, realization tile);
+//     all lanes of a warp look at the same (cell,f) element, so the per-element sampler set-up is
+//     staged once per CTA in shared memory (non-empty elements only: 83% of the grid has N == 0)
+//     and the sampler class branch is warp-uniform;
+//   * the (M,q,z) reduction lives in per-thread registers -> per-chunk partial sums in HBM ->
+//     a fixed-order final reduction (bit-reproducible; no floating-point atomics);
+//   * the loudest-L selection only ever needs the first few *occupied* cells in rank order.  A prep
+//     pass finds, per frequency, the rank K_f at which the expected number of occupied cells reaches
+//     L + margin; occupied cells with rank < K_f are appended to a small per-(f,r) event bucket and
+//     resolved (sorted by rank, slots handed out with multiplicity) by one warp per (f,r); everything
+//     else is summed straight into the background.  If a bucket overflows or the head turns out to
+//     be too short the call reports HOLO_ERR_OVERFLOW and the host retries with a larger margin.
+#include <cuda_runtime.h>
+
+#include "holo_api.cuh"
+#include "holo_rng.cuh"
+
+namespace holo {
+
+enum {
+    V_GWB = 0,
+    V_LOUD_PLAIN = HOLO_LOUDEST_PLAIN,
+    V_LOUD_PAR = HOLO_LOUDEST_PAR,
+    V_LOUD_PAR_REDZ = HOLO_LOUDEST_PAR_REDZ,
+    V_SSBG = 4,
+    V_SSBG_PAR = 5,
+};
+
+__host__ __device__ constexpr int nacc_of(int variant) {
+    return variant == V_LOUD_PAR_REDZ ? 8 : ((variant == V_LOUD_PAR || variant == V_SSBG_PAR) ? 4 : 1);
+}
+__host__ __device__ constexpr bool has_events(int v) {
+    return v == V_LOUD_PLAIN || v == V_LOUD_PAR || v == V_LOUD_PAR_REDZ;
+}
+__host__ __device__ constexpr bool has_max(int v) { return v == V_SSBG || v == V_SSBG_PAR; }
+
+constexpr int RZ_THREADS = 256;      // realizations per CTA (max)
+constexpr int SUB = 512;             // cells scanned per staging pass (chunk granularity)
+constexpr int FGROUP = 4;            // frequencies per CTA (4 doubles = one 32 B sector per cell)
+constexpr int STREAM_GWB = 1, STREAM_LOUD = 2, STREAM_SSBG = 3, STREAM_BULK = 4, STREAM_ECC = 5;
+
+struct Event {
+    int rank;
+    int cell;
+    double n;
+};
+
+struct RealizeArgs {
+    const double* number;     // (ncell, F)
+    const double* h2fdf;      // (ncell, F)
+    const int32_t* rank;      // (ncell,)  rank of each cell (events variants)
+    const int32_t* kf;        // (F,)      head length per frequency
+    const double* mt;         // (Mb,)
+    const double* mr;         // (Qb,)
+    const double* rz;         // (Zb,)
+    const double* redz_final; // (ncell, F)
+    const double* dcom_final;
+    const double* sepa;
+    const double* angs;
+    const double* counts;     // (R, F, ncell) or NULL
+    double* partial;          // (nchunk, F, NACC, R)
+    double* pmax;             // (nchunk, F, R)        ss_bg variants
+    int32_t* pidx;            // (nchunk, F, R)
+    Event* events;            // (F, R, cap)
+    int32_t* evcount;         // (F, R)
+    int64_t ncell;
+    int64_t chunk;            // cells per CTA
+    int Qb, Zb, F, R, cap;
+    int64_t r0;
+    uint32_t k0, k1;
+    double thresh;
+};
+
+template <int NACC>
+struct Entry {
+    DrawPrep prep;
+    double h;
+    double w[NACC > 1 ? NACC - 1 : 1];
+    int cell;
+    int head;   // 1: occupied draws go to the event bucket (rank < K_f); also carries the rank
+};
+
+template <int VARIANT>
+__global__ void __launch_bounds__(RZ_THREADS)
+realize_kernel(RealizeArgs a) {
+    constexpr int NACC = nacc_of(VARIANT);
+    using Ent = Entry<NACC>;
+    constexpr int SUBV = NACC > 4 ? SUB / 2 : SUB;   // keep the staging buffer under 48 KB static smem
+    __shared__ Ent s_ent[SUBV];
+    __shared__ int s_wcount[RZ_THREADS / 32];
+    __shared__ int s_total;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarp = blockDim.x >> 5;
+    const int chunk_id = blockIdx.x;
+    const int f0 = blockIdx.y * FGROUP;
+    const int r = blockIdx.z * blockDim.x + tid;      // local realization
+    const bool live = r < a.R;
+    const int64_t c_lo = (int64_t)chunk_id * a.chunk;
+    int64_t c_hi = c_lo + a.chunk;
+    if (c_hi > a.ncell) c_hi = a.ncell;
+    const int nf = (a.F - f0) < FGROUP ? (a.F - f0) : FGROUP;
+    const bool supplied = a.counts != nullptr;
+
+    double acc[FGROUP][NACC];
+    double vmax[FGROUP];
+    int imax[FGROUP];
+#pragma unroll
+    for (int fi = 0; fi < FGROUP; ++fi) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[fi][k] = 0.0;
+        vmax[fi] = 0.0;
+        imax[fi] = -1;
+    }
+
+    DrawKey key;
+    key.k0 = a.k0; key.k1 = a.k1;
+    key.real = (uint32_t)(a.r0 + r);
+    key.stream = has_events(VARIANT) ? STREAM_LOUD : (has_max(VARIANT) ? STREAM_SSBG : STREAM_GWB);
+
+    for (int64_t cb = c_lo; cb < c_hi; cb += SUBV) {
+#pragma unroll
+        for (int fi = 0; fi < FGROUP; ++fi) {
+            if (fi >= nf) break;
+            const int f = f0 + fi;
+            // ---- stage the non-empty elements of cells [cb, cb+SUB) at frequency f, in cell order
+            __syncthreads();   // previous pass fully consumed
+            int base = 0;
+            for (int off = 0; off < SUBV; off += blockDim.x) {
+                int64_t c = cb + off + tid;
+                double lam = 0.0, h = 0.0;
+                bool keep = false;
+                if (c < c_hi && off + tid < SUBV) {
+                    lam = a.number[c * a.F + f];
+                    h = a.h2fdf[c * a.F + f];
+                    keep = supplied || (lam > 0.0);
+                    if (VARIANT == V_LOUD_PAR_REDZ) keep = keep && (h != 0.0);   // pyx:1727
+                }
+                unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (lane == 0) s_wcount[warp] = __popc(bal);
+                __syncthreads();
+                int pos = base;
+                for (int w = 0; w < warp; ++w) pos += s_wcount[w];
+                pos += __popc(bal & ((1u << lane) - 1u));
+                if (keep) {
+                    Ent e;
+                    e.prep = prep_draw(lam, a.thresh);
+                    e.h = h;
+                    e.cell = (int)c;
+                    e.head = 0;
+                    if (has_events(VARIANT)) {
+                        int rk = a.rank[c];
+                        e.head = (rk < a.kf[f]) ? 1 : 0;
+                    }
+                    if (NACC > 1) {
+                        int zz = (int)(c % a.Zb);
+                        int64_t mq = c / a.Zb;
+                        int qq = (int)(mq % a.Qb);
+                        int mm = (int)(mq / a.Qb);
+                        e.w[0] = a.mt[mm];
+                        if (NACC > 2) { e.w[1] = a.mr[qq]; e.w[2] = a.rz[zz]; }
+                        if (NACC > 4) {
+                            e.w[3] = a.redz_final[c * a.F + f];
+                            e.w[4] = a.dcom_final[c * a.F + f];
+                            e.w[5] = a.sepa[c * a.F + f];
+                            e.w[6] = a.angs[c * a.F + f];
+                        }
+                    }
+                    s_ent[pos] = e;
+                }
+                if (tid == 0) {
+                    int tot = 0;
+                    for (int w = 0; w < nwarp; ++w) tot += s_wcount[w];
+                    s_total = base + tot;
+                }
+                __syncthreads();
+                base = s_total;
+            }
+            const int count = base;
+            if (!live) continue;
+
+            // ---- every thread (= realization) walks the staged list
+            for (int i = 0; i < count; ++i) {
+                const Ent& e = s_ent[i];
+                double n;
+                if (supplied) {
+                    n = a.counts[((int64_t)r * a.F + f) * a.ncell + e.cell];
+                } else {
+                    uint64_t idx = (uint64_t)e.cell * (uint64_t)a.F + (uint64_t)f;
+                    key.idx_lo = (uint32_t)idx;
+                    key.idx_hi = (uint32_t)(idx >> 32);
+                    n = draw_count(e.prep, key);
+                }
+                if (VARIANT == V_GWB) {
+                    acc[fi][0] += n * e.h;                                   // pyx:891, 895
+                } else if (has_max(VARIANT)) {
+                    double cur = e.h;
+                    if (cur > vmax[fi] && n > 0.0) { vmax[fi] = cur; imax[fi] = e.cell; }   // pyx:993, 1134
+                    double nc = n * cur;
+                    acc[fi][0] += nc;                                        // pyx:998, 1139
+                    if (NACC > 1) {
+#pragma unroll
+                        for (int k = 1; k < NACC; ++k) acc[fi][k] += nc * e.w[k - 1];
+                    }
+                } else {
+                    if (n < 1.0) continue;                                   // pyx:1333, 1490, 1727
+                    if (e.head) {
+                        int slot = atomicAdd(&a.evcount[(int64_t)f * a.R + r], 1);
+                        if (slot < a.cap) {
+                            Event ev;
+                            ev.rank = a.rank[e.cell];
+                            ev.cell = e.cell;
+                            ev.n = n;
+                            a.events[((int64_t)f * a.R + r) * a.cap + slot] = ev;
+                        }
+                    } else {
+                        double nc = n * e.h;
+                        acc[fi][0] += nc;                                    // pyx:1342, 1505, 1745
+                        if (NACC > 1) {
+#pragma unroll
+                            for (int k = 1; k < NACC; ++k) acc[fi][k] += nc * e.w[k - 1];
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    if (live) {
+#pragma unroll
+        for (int fi = 0; fi < FGROUP; ++fi) {
+            if (fi >= nf) break;
+            const int f = f0 + fi;
+            int64_t pb = ((int64_t)chunk_id * a.F + f) * NACC;
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) a.partial[(pb + k) * a.R + r] = acc[fi][k];
+            if (has_max(VARIANT)) {
+                int64_t mb = ((int64_t)chunk_id * a.F + f) * a.R + r;
+                a.pmax[mb] = vmax[fi];
+                a.pidx[mb] = imax[fi];
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Head preparation for the loudest variants
+// -------------------------------------------------------------------------------------------------
+__global__ void rank_inverse_kernel(const int32_t* __restrict__ order, int64_t ncell,
+                                    int32_t* __restrict__ rank) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < ncell;
+         p += (int64_t)gridDim.x * blockDim.x)
+        rank[order[p]] = (int32_t)p;
+}
+
+constexpr int HEAD_ROWS = 1024;   // rank positions per block
+
+// bsum[blk][f] = sum over rank positions of the block of P(cell occupied) at frequency f
+__global__ void __launch_bounds__(256)
+head_sum_kernel(const double* __restrict__ number, const double* __restrict__ h2fdf,
+                const int32_t* __restrict__ order, int64_t ncell, int F, double thresh, int need_h,
+                int supplied, double* __restrict__ bsum) {
+    extern __shared__ double s_sum[];
+    for (int f = threadIdx.x; f < F; f += blockDim.x) s_sum[f] = 0.0;
+    __syncthreads();
+    int64_t p0 = (int64_t)blockIdx.x * HEAD_ROWS;
+    int64_t nel = (int64_t)HEAD_ROWS * F;
+    for (int64_t i = threadIdx.x; i < nel; i += blockDim.x) {
+        int64_t p = p0 + i / F;
+        int f = (int)(i % F);
+        if (p >= ncell) break;
+        int64_t c = order[p];
+        double lam = number[c * F + f];
+        bool elig = (lam > 0.0);
+        if (need_h) elig = elig && (h2fdf[c * F + f] != 0.0);
+        (void)supplied;   // supplied counts are assumed to be draws of `number`: same head estimate
+        double pocc = 0.0;
+        if (elig) pocc = (lam > thresh) ? 1.0 : -expm1(-lam);
+        if (pocc > 0.0) atomicAdd(&s_sum[f], pocc);
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += blockDim.x) bsum[(int64_t)blockIdx.x * F + f] = s_sum[f];
+}
+
+__global__ void head_cut_kernel(const double* __restrict__ bsum, int nblk, int F, int64_t ncell,
+                                double target, int32_t* __restrict__ kf) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    double cum = 0.0;
+    int64_t k = ncell;
+    for (int b = 0; b < nblk; ++b) {
+        cum += bsum[(int64_t)b * F + f];
+        if (cum >= target) { k = (int64_t)(b + 1) * HEAD_ROWS; break; }
+    }
+    if (k > ncell) k = ncell;
+    kf[f] = (int32_t)k;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Resolver: one warp per (f, r) hands out the L slots in rank order (with multiplicity) and sums
+// what is left of the head into the background.
+// -------------------------------------------------------------------------------------------------
+struct ResolveArgs {
+    const Event* events;
+    const int32_t* evcount;
+    const int32_t* kf;
+    const double* h2fdf;
+    const double* mt;
+    const double* mr;
+    const double* rz;
+    const double* redz_final;
+    const double* dcom_final;
+    const double* sepa;
+    const double* angs;
+    double* hc2ss;    // (F,R,L)
+    double* sspar;    // (4,F,R,L)
+    double* lspar;    // (3,F,R)
+    int64_t* ssidx;   // (3,F,R,L)
+    double* rem;      // (F, NACC, R)
+    int32_t* flags;   // [0]: bucket overflow, [1]: head too short
+    int64_t ncell;
+    int Qb, Zb, F, R, L, cap;
+};
+
+constexpr int RES_WARPS = 4;
+
+template <int VARIANT>
+__global__ void __launch_bounds__(RES_WARPS * 32)
+resolve_kernel(ResolveArgs a) {
+    constexpr int NACC = nacc_of(VARIANT);
+    extern __shared__ unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t fr = (int64_t)blockIdx.x * RES_WARPS + warp;
+    if (fr >= (int64_t)a.F * a.R) return;
+    const int f = (int)(fr / a.R);
+    const int r = (int)(fr % a.R);
+    Event* raw = reinterpret_cast<Event*>(s_raw) + (size_t)warp * 2 * a.cap;
+    Event* ev = raw + a.cap;
+
+    int cnt = a.evcount[fr];
+    if (cnt > a.cap) {
+        if (lane == 0) atomicOr(&a.flags[0], 1);
+        cnt = a.cap;
+    }
+    for (int i = lane; i < cnt; i += 32) raw[i] = a.events[fr * a.cap + i];
+    __syncwarp();
+    // The bucket was filled with atomics, i.e. in arbitrary order: sort it by rank (ranks are unique)
+    // so that everything below is bit-reproducible.  cnt is ~L + margin, a counting sort is plenty.
+    for (int i = lane; i < cnt; i += 32) {
+        int rk = raw[i].rank, pos = 0;
+        for (int j = 0; j < cnt; ++j) pos += (raw[j].rank < rk) ? 1 : 0;
+        ev[pos] = raw[i];
+    }
+    __syncwarp();
+
+    double rem[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) rem[k] = 0.0;
+    double ls[4] = {0.0, 0.0, 0.0, 0.0};
+    int ll = 0;
+    int next = 0;   // first event that did not (fully) go into the loudest slots
+
+    // walk the head in rank order until the L slots are full
+    while (ll < a.L && next < cnt) {
+        Event e = ev[next];
+        ++next;
+        const int64_t c = e.cell;
+        const double cur = a.h2fdf[c * a.F + f];
+        int zz = (int)(c % a.Zb);
+        int64_t mq = c / a.Zb;
+        int qq = (int)(mq % a.Qb);
+        int mm = (int)(mq / a.Qb);
+        double num = e.n;
+        // `while (ll < L) and (num > 0)`  pyx:1338-1341, 1493-1503, 1730-1742
+        while (ll < a.L && num > 0.0) {
+            if (lane == 0) {
+                int64_t o = fr * a.L + ll;
+                a.hc2ss[o] = cur;
+                if (VARIANT == V_LOUD_PAR) {
+                    int64_t st = (int64_t)a.F * a.R * a.L;
+                    a.ssidx[o] = mm; a.ssidx[st + o] = qq; a.ssidx[2 * st + o] = zz;
+                }
+                if (VARIANT == V_LOUD_PAR_REDZ) {
+                    int64_t st = (int64_t)a.F * a.R * a.L;
+                    a.sspar[o] = a.mt[mm];
+                    a.sspar[st + o] = a.mr[qq];
+                    a.sspar[2 * st + o] = a.rz[zz];
+                    a.sspar[3 * st + o] = a.redz_final[c * a.F + f];
+                }
+            }
+            if (VARIANT == V_LOUD_PAR) {
+                ls[0] += cur; ls[1] += cur * a.mt[mm]; ls[2] += cur * a.mr[qq]; ls[3] += cur * a.rz[zz];
+            }
+            num -= 1.0;
+            ll += 1;
+        }
+        // what is left of this cell goes to the background (pyx:1342, 1505-1508, 1745-1752)
+        double nc = num * cur;
+        rem[0] += nc;
+        if (NACC > 1) {
+            rem[1] += nc * a.mt[mm];
+            if (NACC > 2) { rem[2] += nc * a.mr[qq]; rem[3] += nc * a.rz[zz]; }
+            if (NACC > 4) {
+                rem[4] += nc * a.redz_final[c * a.F + f];
+                rem[5] += nc * a.dcom_final[c * a.F + f];
+                rem[6] += nc * a.sepa[c * a.F + f];
+                rem[7] += nc * a.angs[c * a.F + f];
+            }
+        }
+    }
+    // unfilled slots stay zero (outputs are zero-initialised by the host wrapper)
+    if (ll < a.L && a.kf[f] < a.ncell && lane == 0) atomicOr(&a.flags[1], 1);
+
+    // the rest of the head is pure background: lane-strided sums in rank order + fixed butterfly
+    double part[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) part[k] = 0.0;
+    for (int i = next + lane; i < cnt; i += 32) {
+        Event e = ev[i];
+        const int64_t c = e.cell;
+        double nc = e.n * a.h2fdf[c * a.F + f];
+        part[0] += nc;
+        if (NACC > 1) {
+            int zz = (int)(c % a.Zb);
+            int64_t mq = c / a.Zb;
+            int qq = (int)(mq % a.Qb);
+            int mm = (int)(mq / a.Qb);
+            part[1] += nc * a.mt[mm];
+            if (NACC > 2) { part[2] += nc * a.mr[qq]; part[3] += nc * a.rz[zz]; }
+            if (NACC > 4) {
+                part[4] += nc * a.redz_final[c * a.F + f];
+                part[5] += nc * a.dcom_final[c * a.F + f];
+                part[6] += nc * a.sepa[c * a.F + f];
+                part[7] += nc * a.angs[c * a.F + f];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+        double v = part[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) a.rem[((int64_t)f * NACC + k) * a.R + r] = rem[k] + v;
+    }
+    if (VARIANT == V_LOUD_PAR && lane == 0) {
+        int64_t st = (int64_t)a.F * a.R;
+        a.lspar[fr] = ls[1] / ls[0];              // pyx:1513-1515
+        a.lspar[st + fr] = ls[2] / ls[0];
+        a.lspar[2 * st + fr] = ls[3] / ls[0];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Final fixed-order reduction over chunks
+// -------------------------------------------------------------------------------------------------
+struct FinalArgs {
+    const double* partial;   // (nchunk, F, NACC, R)
+    const double* rem;       // (F, NACC, R) or NULL
+    const double* pmax;
+    const int32_t* pidx;
+    const double* h2fdf;
+    const double* mt;
+    const double* mr;
+    const double* rz;
+    double* out0;            // gwb / hc2bg (F,R)
+    double* bgpar;           // (NACC-1, F, R)
+    double* hc2ss;           // ss_bg: (F,R)
+    double* sspar;           // ss_bg_par: (3,F,R)
+    int64_t* ssidx;          // ss_bg: (3,F,R)
+    int32_t* flags;          // [2]: ss_bg_par found no source
+    int nchunk, Qb, Zb, F, R;
+};
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256)
+final_kernel(FinalArgs a) {
+    constexpr int NACC = nacc_of(VARIANT);
+    int64_t fr = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (fr >= (int64_t)a.F * a.R) return;
+    int f = (int)(fr / a.R), r = (int)(fr % a.R);
+    double s[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) s[k] = 0.0;
+    double vmax = 0.0;
+    int imax = -1;
+    for (int ch = 0; ch < a.nchunk; ++ch) {
+        int64_t pb = ((int64_t)ch * a.F + f) * NACC;
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) s[k] += a.partial[(pb + k) * a.R + r];
+        if (has_max(VARIANT)) {
+            int64_t mb = ((int64_t)ch * a.F + f) * a.R + r;
+            double v = a.pmax[mb];
+            if (v > vmax) { vmax = v; imax = a.pidx[mb]; }
+        }
+    }
+    if (a.rem) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) s[k] += a.rem[((int64_t)f * NACC + k) * a.R + r];
+    }
+    int64_t st = (int64_t)a.F * a.R;
+    if (has_max(VARIANT)) {
+        int zz = -1, qq = -1, mm = -1;
+        if (imax >= 0) {
+            zz = imax % a.Zb;
+            int mq = imax / a.Zb;
+            qq = mq % a.Qb;
+            mm = mq / a.Qb;
+        }
+        a.hc2ss[fr] = vmax;                         // pyx:1003-1008, 1145-1165
+        a.out0[fr] = s[0] - vmax;
+        a.ssidx[fr] = mm; a.ssidx[st + fr] = qq; a.ssidx[2 * st + fr] = zz;
+        if (VARIANT == V_SSBG_PAR) {
+            if (imax < 0) {
+                atomicOr(&a.flags[2], 1);           // pyx:1157-1158 bare `raise`
+            } else {
+                double hm = a.h2fdf[(int64_t)imax * a.F + f];
+                double den = s[0] - vmax;
+                a.bgpar[fr] = (s[1] - hm * a.mt[mm]) / den;
+                a.bgpar[st + fr] = (s[2] - hm * a.mr[qq]) / den;
+                a.bgpar[2 * st + fr] = (s[3] - hm * a.rz[zz]) / den;
+                a.sspar[fr] = a.mt[mm];
+                a.sspar[st + fr] = a.mr[qq];
+                a.sspar[2 * st + fr] = a.rz[zz];
+            }
+        }
+    } else {
+        a.out0[fr] = s[0];
+        if (NACC > 1) {
+#pragma unroll
+            for (int k = 1; k < NACC; ++k) a.bgpar[(k - 1) * st + fr] = s[k] / s[0];   // pyx:1509-1512, 1761-1767
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// poisson_as_needed (gravwaves.py:666-691): elementwise, normal branch floored
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bulk_poisson_kernel(const double* __restrict__ lam, int64_t n, uint32_t k0, uint32_t k1,
+                    uint32_t stream_id, double thresh, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double l = lam[i];
+        double v = 0.0;
+        if (l > 0.0) {
+            DrawPrep p = prep_draw(l, thresh);
+            DrawKey key;
+            key.k0 = k0; key.k1 = k1;
+            key.idx_lo = (uint32_t)i; key.idx_hi = (uint32_t)((uint64_t)i >> 32);
+            key.real = stream_id; key.stream = STREAM_BULK;
+            v = draw_count(p, key);
+            if (p.cls == CLS_NORMAL) v = floor(v);
+        }
+        out[i] = v;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-side planning
+// -------------------------------------------------------------------------------------------------
+struct Plan {
+    int threads, ntiles, nfg, nchunk;
+    int64_t chunk;
+};
+
+static Plan make_plan(int64_t ncell, int F, int R) {
+    Plan p;
+    p.threads = R >= RZ_THREADS ? RZ_THREADS : ((R + 31) / 32) * 32;
+    if (p.threads < 32) p.threads = 32;
+    p.ntiles = (R + p.threads - 1) / p.threads;
+    p.nfg = (F + FGROUP - 1) / FGROUP;
+    // The cell chunking must not depend on R (or on the realization tiling): per-chunk partial sums are
+    // combined in a fixed order, so a fixed chunking makes hc2 bit-identical however the realizations
+    // are partitioned over launches / GPUs.  ~128 chunks x (F/4) x tiles CTAs fills 148 SMs several times.
+    int64_t nchunk = 128;
+    int64_t chunk = (ncell + nchunk - 1) / nchunk;
+    chunk = ((chunk + SUB - 1) / SUB) * SUB;
+    if (chunk < SUB) chunk = SUB;
+    p.chunk = chunk;
+    p.nchunk = (int)((ncell + chunk - 1) / chunk);
+    if (p.nchunk < 1) p.nchunk = 1;
+    return p;
+}
+
+static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+
+static int auto_cap(int L, double margin) {
+    double target = L + margin;
+    int cap = 64;
+    while (cap < 2.0 * target + 64.0) cap *= 2;
+    return cap;
+}
+
+static double auto_margin(int L) { return 8.0 * sqrt((double)L) + 24.0; }
+
+struct Workspace {
+    unsigned char* base;
+    int64_t used, size;
+    void* take(int64_t bytes) {
+        void* p = base ? base + used : nullptr;
+        used += align256(bytes);
+        return p;
+    }
+};
+
+struct Layout {
+    double* partial; double* pmax; int32_t* pidx; Event* events; int32_t* evcount; double* rem;
+    int32_t* flags; int32_t* kf; int32_t* rank; double* bsum;
+    int64_t total;
+};
+
+static Layout carve(void* ws, int variant, int64_t ncell, int F, int R, int cap, const Plan& p) {
+    Workspace w{(unsigned char*)ws, 0, 0};
+    int nacc = nacc_of(variant);
+    Layout l{};
+    l.flags = (int32_t*)w.take(4 * sizeof(int32_t));
+    l.partial = (double*)w.take(sizeof(double) * (int64_t)p.nchunk * F * nacc * R);
+    if (has_max(variant)) {
+        l.pmax = (double*)w.take(sizeof(double) * (int64_t)p.nchunk * F * R);
+        l.pidx = (int32_t*)w.take(sizeof(int32_t) * (int64_t)p.nchunk * F * R);
+    }
+    if (has_events(variant)) {
+        l.events = (Event*)w.take(sizeof(Event) * (int64_t)F * R * cap);
+        l.evcount = (int32_t*)w.take(sizeof(int32_t) * (int64_t)F * R);
+        l.rem = (double*)w.take(sizeof(double) * (int64_t)F * nacc * R);
+        l.kf = (int32_t*)w.take(sizeof(int32_t) * F);
+        l.rank = (int32_t*)w.take(sizeof(int32_t) * ncell);
+        int nblk = (int)((ncell + HEAD_ROWS - 1) / HEAD_ROWS);
+        l.bsum = (double*)w.take(sizeof(double) * (int64_t)nblk * F);
+    }
+    l.total = w.used;
+    return l;
+}
+
+template <int VARIANT>
+static int launch_realize(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
+    dim3 grid(p.nchunk, p.nfg, p.ntiles);
+    realize_kernel<VARIANT><<<grid, p.threads, 0, st>>>(ra); holo::count_launches(1);
+    return holo_check_launch("realize_kernel");
+}
+
+}  // namespace holo
+
+using namespace holo;
+
+extern "C" {
+
+int64_t holo_realize_workspace_bytes(int kind, int64_t ncell, int F, int R) {
+    if (ncell <= 0 || F <= 0 || R <= 0) return 256;
+    Plan p = make_plan(ncell, F, R);
+    int variant = kind == HOLO_REALIZE_SSBG_PAR ? V_SSBG_PAR : (kind == HOLO_REALIZE_SSBG ? V_SSBG : V_GWB);
+    Layout l = carve(nullptr, variant, ncell, F, R, 0, p);
+    return l.total;
+}
+
+int64_t holo_loudest_workspace_bytes(int variant, int64_t ncell, int F, int R, int L, int bucket_cap) {
+    if (ncell <= 0 || F <= 0 || R <= 0) return 256;
+    Plan p = make_plan(ncell, F, R);
+    int cap = bucket_cap > 0 ? bucket_cap : auto_cap(L, auto_margin(L));
+    Layout l = carve(nullptr, variant, ncell, F, R, cap, p);
+    return l.total;
+}
+
+int holo_sam_poisson_gwb(const double* number, const double* h2fdf, int64_t ncell, int F, int R,
+                         int64_t r0, uint64_t seed, double normal_threshold, const double* counts,
+                         double* gwb, void* workspace, int64_t workspace_bytes, void* stream) {
+    HOLO_REQUIRE(number && h2fdf && gwb && workspace, "holo_sam_poisson_gwb: NULL argument");
+    HOLO_REQUIRE(ncell > 0 && F > 0 && R > 0, "holo_sam_poisson_gwb: bad shape");
+    HOLO_REQUIRE(ncell < 2147483647LL, "holo_sam_poisson_gwb: too many cells");
+    cudaStream_t st = (cudaStream_t)stream;
+    Plan p = make_plan(ncell, F, R);
+    Layout l = carve(workspace, V_GWB, ncell, F, R, 0, p);
+    HOLO_REQUIRE(l.total <= workspace_bytes, "holo_sam_poisson_gwb: workspace too small");
+    RealizeArgs ra{};
+    ra.number = number; ra.h2fdf = h2fdf; ra.counts = counts; ra.partial = l.partial;
+    ra.ncell = ncell; ra.chunk = p.chunk; ra.Qb = 1; ra.Zb = 1; ra.F = F; ra.R = R; ra.cap = 0;
+    ra.r0 = r0; ra.k0 = (uint32_t)seed; ra.k1 = (uint32_t)(seed >> 32);
+    ra.thresh = (double)(int64_t)normal_threshold;                       // `long thresh`, pyx:855, 863
+    int rc = launch_realize<V_GWB>(ra, p, st);
+    if (rc) return rc;
+    FinalArgs fa{};
+    fa.partial = l.partial; fa.out0 = gwb; fa.nchunk = p.nchunk; fa.Qb = 1; fa.Zb = 1; fa.F = F; fa.R = R;
+    int64_t nfr = (int64_t)F * R;
+    final_kernel<V_GWB><<<(int)((nfr + 255) / 256), 256, 0, st>>>(fa); holo::count_launches(1);
+    return holo_check_launch("holo_sam_poisson_gwb");
+}
+
+int holo_loudest(const holo_loudest_args* g, void* stream) {
+    HOLO_REQUIRE(g, "holo_loudest: NULL args");
+    const int v = g->variant;
+    HOLO_REQUIRE(v == V_LOUD_PLAIN || v == V_LOUD_PAR || v == V_LOUD_PAR_REDZ, "holo_loudest: bad variant");
+    HOLO_REQUIRE(g->number && g->h2fdf && g->order && g->hc2ss && g->hc2bg && g->workspace,
+                 "holo_loudest: NULL argument");
+    HOLO_REQUIRE(g->Mb > 0 && g->Qb > 0 && g->Zb > 0 && g->F > 0 && g->R > 0 && g->L > 0,
+                 "holo_loudest: bad shape");
+    if (v != V_LOUD_PLAIN) HOLO_REQUIRE(g->mt && g->mr && g->rz && g->bgpar, "holo_loudest: NULL parameter arrays");
+    if (v == V_LOUD_PAR) HOLO_REQUIRE(g->lspar && g->ssidx, "holo_loudest: NULL lspar/ssidx");
+    if (v == V_LOUD_PAR_REDZ)
+        HOLO_REQUIRE(g->redz_final && g->dcom_final && g->sepa && g->angs && g->sspar,
+                     "holo_loudest: NULL redz arrays");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ncell = (int64_t)g->Mb * g->Qb * g->Zb;
+    HOLO_REQUIRE(ncell < 2147483647LL, "holo_loudest: too many cells");
+    const int F = g->F, R = g->R, L = g->L;
+    Plan p = make_plan(ncell, F, R);
+    double margin = g->head_margin > 0 ? g->head_margin : auto_margin(L);
+    int cap = g->bucket_cap > 0 ? g->bucket_cap : auto_cap(L, margin);
+    Layout l = carve(g->workspace, v, ncell, F, R, cap, p);
+    HOLO_REQUIRE(l.total <= g->workspace_bytes, "holo_loudest: workspace too small");
+    size_t res_smem = (size_t)RES_WARPS * 2 * cap * sizeof(Event);
+    HOLO_REQUIRE(res_smem <= 200 * 1024, "holo_loudest: bucket_cap too large");
+
+    const int nacc = nacc_of(v);
+    const int64_t nfr = (int64_t)F * R;
+    HOLO_CUDA(cudaMemsetAsync(l.flags, 0, 4 * sizeof(int32_t), st));
+    HOLO_CUDA(cudaMemsetAsync(l.evcount, 0, sizeof(int32_t) * nfr, st));
+    HOLO_CUDA(cudaMemsetAsync(g->hc2ss, 0, sizeof(double) * nfr * L, st));
+    if (v == V_LOUD_PAR) HOLO_CUDA(cudaMemsetAsync(g->ssidx, 0, sizeof(int64_t) * 3 * nfr * L, st));
+    if (v == V_LOUD_PAR_REDZ) HOLO_CUDA(cudaMemsetAsync(g->sspar, 0, sizeof(double) * 4 * nfr * L, st));
+
+    // ---- head preparation
+    rank_inverse_kernel<<<(int)((ncell + 255) / 256 > 4736 ? 4736 : (ncell + 255) / 256), 256, 0, st>>>(
+        g->order, ncell, l.rank); holo::count_launches(1);
+    int nblk = (int)((ncell + HEAD_ROWS - 1) / HEAD_ROWS);
+    head_sum_kernel<<<nblk, 256, sizeof(double) * F, st>>>(
+        g->number, g->h2fdf, g->order, ncell, F, (double)(int64_t)g->normal_threshold,
+        v == V_LOUD_PAR_REDZ ? 1 : 0, g->counts ? 1 : 0, l.bsum); holo::count_launches(1);
+    head_cut_kernel<<<(F + 63) / 64, 64, 0, st>>>(l.bsum, nblk, F, ncell, (double)L + margin, l.kf); holo::count_launches(1);
+    int rc = holo_check_launch("holo_loudest: head preparation");
+    if (rc) return rc;
+
+    // ---- draws
+    RealizeArgs ra{};
+    ra.number = g->number; ra.h2fdf = g->h2fdf; ra.rank = l.rank; ra.kf = l.kf;
+    ra.mt = g->mt; ra.mr = g->mr; ra.rz = g->rz;
+    ra.redz_final = g->redz_final; ra.dcom_final = g->dcom_final; ra.sepa = g->sepa; ra.angs = g->angs;
+    ra.counts = g->counts; ra.partial = l.partial; ra.events = l.events; ra.evcount = l.evcount;
+    ra.ncell = ncell; ra.chunk = p.chunk; ra.Qb = g->Qb; ra.Zb = g->Zb; ra.F = F; ra.R = R; ra.cap = cap;
+    ra.r0 = g->r0; ra.k0 = (uint32_t)g->seed; ra.k1 = (uint32_t)(g->seed >> 32);
+    ra.thresh = (double)(int64_t)g->normal_threshold;
+    if (v == V_LOUD_PLAIN) rc = launch_realize<V_LOUD_PLAIN>(ra, p, st);
+    else if (v == V_LOUD_PAR) rc = launch_realize<V_LOUD_PAR>(ra, p, st);
+    else rc = launch_realize<V_LOUD_PAR_REDZ>(ra, p, st);
+    if (rc) return rc;
+
+    // ---- resolve the head, then reduce
+    ResolveArgs rs{};
+    rs.events = l.events; rs.evcount = l.evcount; rs.kf = l.kf; rs.h2fdf = g->h2fdf;
+    rs.mt = g->mt; rs.mr = g->mr; rs.rz = g->rz; rs.redz_final = g->redz_final;
+    rs.dcom_final = g->dcom_final; rs.sepa = g->sepa; rs.angs = g->angs;
+    rs.hc2ss = g->hc2ss; rs.sspar = g->sspar; rs.lspar = g->lspar; rs.ssidx = g->ssidx;
+    rs.rem = l.rem; rs.flags = l.flags; rs.ncell = ncell;
+    rs.Qb = g->Qb; rs.Zb = g->Zb; rs.F = F; rs.R = R; rs.L = L; rs.cap = cap;
+    int rblocks = (int)((nfr + RES_WARPS - 1) / RES_WARPS);
+    if (v == V_LOUD_PLAIN) {
+        if (res_smem > 48 * 1024) HOLO_CUDA(cudaFuncSetAttribute(resolve_kernel<V_LOUD_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
+        resolve_kernel<V_LOUD_PLAIN><<<rblocks, RES_WARPS * 32, res_smem, st>>>(rs); holo::count_launches(1);
+    } else if (v == V_LOUD_PAR) {
+        if (res_smem > 48 * 1024) HOLO_CUDA(cudaFuncSetAttribute(resolve_kernel<V_LOUD_PAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
+        resolve_kernel<V_LOUD_PAR><<<rblocks, RES_WARPS * 32, res_smem, st>>>(rs); holo::count_launches(1);
+    } else {
+        if (res_smem > 48 * 1024) HOLO_CUDA(cudaFuncSetAttribute(resolve_kernel<V_LOUD_PAR_REDZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
+        resolve_kernel<V_LOUD_PAR_REDZ><<<rblocks, RES_WARPS * 32, res_smem, st>>>(rs); holo::count_launches(1);
+    }
+    rc = holo_check_launch("holo_loudest: resolve");
+    if (rc) return rc;
+
+    FinalArgs fa{};
+    fa.partial = l.partial; fa.rem = l.rem; fa.out0 = g->hc2bg; fa.bgpar = g->bgpar;
+    fa.nchunk = p.nchunk; fa.Qb = g->Qb; fa.Zb = g->Zb; fa.F = F; fa.R = R;
+    int fblocks = (int)((nfr + 255) / 256);
+    if (v == V_LOUD_PLAIN) final_kernel<V_LOUD_PLAIN><<<fblocks, 256, 0, st>>>(fa);
+    else if (v == V_LOUD_PAR) final_kernel<V_LOUD_PAR><<<fblocks, 256, 0, st>>>(fa);
+    else final_kernel<V_LOUD_PAR_REDZ><<<fblocks, 256, 0, st>>>(fa);
+    holo::count_launches(1);
+    rc = holo_check_launch("holo_loudest: final");
+    if (rc) return rc;
+
+    int32_t flags[4] = {0, 0, 0, 0};
+    HOLO_CUDA(cudaMemcpyAsync(flags, l.flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    HOLO_CUDA(cudaStreamSynchronize(st));
+    if (flags[0] || flags[1]) {
+        set_error("holo_loudest: %s (bucket_cap=%d, head_margin=%g): retry with larger values",
+                  flags[0] ? "event bucket overflow" : "head too short to fill all loudest slots", cap, margin);
+        return HOLO_ERR_OVERFLOW;
+    }
+    return HOLO_OK;
+}
+
+int holo_ss_bg_hc(const double* number, const double* h2fdf, int Mb, int Qb, int Zb, int F, int R,
+                  int64_t r0, uint64_t seed, double normal_threshold, const double* counts,
+                  const double* mt, const double* mr, const double* rz, double* hc2ss, double* hc2bg,
+                  int64_t* ssidx, double* bgpar, double* sspar, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+    HOLO_REQUIRE(number && h2fdf && hc2ss && hc2bg && ssidx && workspace, "holo_ss_bg_hc: NULL argument");
+    HOLO_REQUIRE(Mb > 0 && Qb > 0 && Zb > 0 && F > 0 && R > 0, "holo_ss_bg_hc: bad shape");
+    const bool par = (bgpar != nullptr) || (sspar != nullptr);
+    if (par) HOLO_REQUIRE(mt && mr && rz && bgpar && sspar, "holo_ss_bg_hc: NULL parameter arrays");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ncell = (int64_t)Mb * Qb * Zb;
+    HOLO_REQUIRE(ncell < 2147483647LL, "holo_ss_bg_hc: too many cells");
+    const int v = par ? V_SSBG_PAR : V_SSBG;
+    Plan p = make_plan(ncell, F, R);
+    Layout l = carve(workspace, v, ncell, F, R, 0, p);
+    HOLO_REQUIRE(l.total <= workspace_bytes, "holo_ss_bg_hc: workspace too small");
+    HOLO_CUDA(cudaMemsetAsync(l.flags, 0, 4 * sizeof(int32_t), st));
+    RealizeArgs ra{};
+    ra.number = number; ra.h2fdf = h2fdf; ra.mt = mt; ra.mr = mr; ra.rz = rz; ra.counts = counts;
+    ra.partial = l.partial; ra.pmax = l.pmax; ra.pidx = l.pidx;
+    ra.ncell = ncell; ra.chunk = p.chunk; ra.Qb = Qb; ra.Zb = Zb; ra.F = F; ra.R = R;
+    ra.r0 = r0; ra.k0 = (uint32_t)seed; ra.k1 = (uint32_t)(seed >> 32);
+    ra.thresh = (double)(int64_t)normal_threshold;
+    int rc = par ? launch_realize<V_SSBG_PAR>(ra, p, st) : launch_realize<V_SSBG>(ra, p, st);
+    if (rc) return rc;
+    FinalArgs fa{};
+    fa.partial = l.partial; fa.pmax = l.pmax; fa.pidx = l.pidx; fa.h2fdf = h2fdf;
+    fa.mt = mt; fa.mr = mr; fa.rz = rz; fa.out0 = hc2bg; fa.bgpar = bgpar; fa.hc2ss = hc2ss;
+    fa.sspar = sspar; fa.ssidx = ssidx; fa.flags = l.flags;
+    fa.nchunk = p.nchunk; fa.Qb = Qb; fa.Zb = Zb; fa.F = F; fa.R = R;
+    int64_t nfr = (int64_t)F * R;
+    int fblocks = (int)((nfr + 255) / 256);
+    if (par) final_kernel<V_SSBG_PAR><<<fblocks, 256, 0, st>>>(fa);
+    else final_kernel<V_SSBG><<<fblocks, 256, 0, st>>>(fa);
+    holo::count_launches(1);
+    rc = holo_check_launch("holo_ss_bg_hc");
+    if (rc) return rc;
+    if (par) {
+        int32_t flags[4] = {0, 0, 0, 0};
+        HOLO_CUDA(cudaMemcpyAsync(flags, l.flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        HOLO_CUDA(cudaStreamSynchronize(st));
+        if (flags[2]) {
+            set_error("holo_ss_bg_hc: no single source found at some (frequency, realization)");
+            return HOLO_ERR_OVERFLOW;
+        }
+    }
+    return HOLO_OK;
+}
+
+int holo_poisson_as_needed(const double* lam, int64_t n, uint64_t seed, uint64_t stream_id,
+                           double normal_threshold, double* out, void* stream) {
+    HOLO_REQUIRE(lam && out && n >= 0, "holo_poisson_as_needed: bad argument");
+    if (n == 0) return HOLO_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    bulk_poisson_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        lam, n, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)stream_id, normal_threshold, out); holo::count_launches(1);
+    return holo_check_launch("holo_poisson_as_needed");
+}
+
+}  // extern "C"

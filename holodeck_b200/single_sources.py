@@ -1,0 +1,125 @@
+"""Single-source / background split (hot-path subset of ``holodeck/single_sources.py``).
+
+* :func:`ss_gws_redz` (``single_sources.py:40-173``) -- what ``sam.gwb`` and ``librarian.run_model`` call
+* :func:`ss_gws`      (``single_sources.py:177-275``) -- same without final redshifts
+
+Arrays may be numpy or CUDA ``torch`` tensors; the per-bin strain, rank ordering, Poisson draws and
+loudest-source selection all run on the device.  The plotting / example helpers and the older
+``loudest_by_cython`` / ``ss_by_*`` variants of the reference are out of scope.
+"""
+import numpy as np
+
+import holodeck_b200 as holo
+from holodeck_b200 import _lib, utils, gravwaves, cyutils
+
+
+def _rank_order(h2fdf, shape):
+    """Bins sorted from largest to smallest h2fdf at the FIRST frequency (``single_sources.py:89-93``).
+
+    The reference uses ``np.argsort`` (unstable quicksort) on ``-h2fdf[...,0]``; ties (the many bins
+    with h=0) come out in an implementation-defined order there.  Here ties keep ascending bin index
+    (stable sort), which is one of the orders the reference may produce.
+    Returns (msort, qsort, zsort) as CUDA int64 tensors.
+    """
+    import torch
+    _, Qb, Zb = shape
+    key = -h2fdf[..., 0].reshape(-1)
+    indices = torch.sort(key, stable=True).indices
+    zsort = indices % Zb
+    mq = indices // Zb
+    return mq // Qb, mq % Qb, zsort
+
+
+def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=None, r0=0, _precomputed=None):
+    """Strain of the `loudest` loudest single sources and of the background, per frequency and realization.
+
+    Parameters mirror ``single_sources.ss_gws_redz`` (``single_sources.py:40-85``):
+    ``edges`` (4,) list of edge arrays (M), (Q), (Z), (F+1) in orbital observer-frame frequency;
+    ``redz`` (M,Q,Z,F) final redshifts at grid edges; ``number`` (M-1,Q-1,Z-1,F) binaries per bin;
+    ``realize`` integer number of realizations.
+
+    Returns ``hc_ss`` (F,R,L), ``hc_bg`` (F,R) and, if ``params``, ``sspar`` (4,F,R,L), ``bgpar`` (7,F,R)
+    (numpy arrays).
+    """
+    import torch
+    _lib.require_gpu()
+    edges_np = [np.asarray(ee.cpu()) if _lib.is_device_array(ee) else np.asarray(ee, dtype=float) for ee in edges]
+    # All other bin midpoints
+    mt = utils.midpoints(edges_np[0])   #: total mass
+    mr = utils.midpoints(edges_np[1])   #: mass ratio
+    rz = utils.midpoints(edges_np[2])   #: initial redshift
+    shape = (mt.size, mr.size, rz.size)
+
+    redz_d = _lib.to_dev(redz)
+    number_d = _lib.to_dev(number)
+
+    # hsfdf = hsamp^2 * f/df  (and the params=True glue of single_sources.py:112-139, same kernel)
+    if _precomputed is not None:
+        strain = _precomputed
+    else:
+        strain = gravwaves._char_strain_sq(edges_np, redz_d, params=bool(params))
+    h2fdf = strain["h2fdf"]
+
+    # indices of bins sorted by h2fdf, just for the first frequency
+    msort, qsort, zsort = _rank_order(h2fdf, shape)
+
+    if bool(torch.any(torch.logical_and(redz_d < 0, redz_d != -1))):
+        err = int(torch.sum(torch.logical_and(redz_d < 0, redz_d != -1)))
+        err = f"{err} redz < 0 and !=-1 found in redz, in ss_gws_redz()"
+        raise ValueError(err)
+
+    if not utils.isinteger(realize):
+        raise Exception("`realize` ({}) must be an integer!")
+
+    if params is True or params:
+        hc2ss, hc2bg, sspar, bgpar = cyutils.loudest_hc_and_par_from_sorted_redz(
+            number_d, h2fdf, realize, loudest,
+            mt, mr, rz, strain["zmid"], strain["dcom"], strain["sepa"], strain["angs"],
+            msort, qsort, zsort, seed=seed, r0=r0, device=True)
+        hc_ss = torch.sqrt(hc2ss).cpu().numpy()
+        hc_bg = torch.sqrt(hc2bg).cpu().numpy()
+        sspar = sspar.cpu().numpy()
+        bgpar = bgpar.cpu().numpy()
+        # check that all final redshifts are positive or -1
+        if np.any(np.logical_and(sspar[3] < 0, sspar[3] != -1)):
+            err = np.sum(np.logical_and(sspar[3] < 0, sspar[3] != -1))
+            err = f"check 1: {err} out of {sspar[3].size} sspar[3] are negative and not -1 in sings.ss_gws_redz()"
+            raise ValueError(err)
+        return hc_ss, hc_bg, sspar, bgpar
+
+    hc2ss, hc2bg = cyutils.loudest_hc_from_sorted(number_d, h2fdf, realize, loudest, msort, qsort, zsort,
+                                                  seed=seed, r0=r0, device=True)
+    hc_ss = torch.sqrt(hc2ss).cpu().numpy()
+    hc_bg = torch.sqrt(hc2bg).cpu().numpy()
+    return hc_ss, hc_bg
+
+
+def ss_gws(edges, number, realize, loudest=1, params=False, *, seed=None, r0=0):
+    """As :func:`ss_gws_redz` with every bin at its initial redshift (``single_sources.py:177-275``).
+
+    With ``params=True`` returns ``hc_ss, hc_bg, sspar (3,F,R,L), bgpar (3,F,R)`` where ``sspar`` holds
+    the (M, q, z) bin-centre values of each loud source (``single_sources.py:255-263``).
+    """
+    import torch
+    _lib.require_gpu()
+    edges_np = [np.asarray(ee.cpu()) if _lib.is_device_array(ee) else np.asarray(ee, dtype=float) for ee in edges]
+    mt = utils.midpoints(edges_np[0])
+    mr = utils.midpoints(edges_np[1])
+    rz = utils.midpoints(edges_np[2])
+    shape = (mt.size, mr.size, rz.size)
+    number_d = _lib.to_dev(number)
+    h2fdf = gravwaves._char_strain_sq(edges_np, None)["h2fdf"]
+    msort, qsort, zsort = _rank_order(h2fdf, shape)
+    if not utils.isinteger(realize):
+        raise Exception("`realize` ({}) must be an integer!")
+    if params:
+        hc2ss, hc2bg, lspar, bgpar, ssidx = cyutils.loudest_hc_and_par_from_sorted(
+            number_d, h2fdf, realize, loudest, mt, mr, rz, msort, qsort, zsort, seed=seed, r0=r0, device=True)
+        ssidx = ssidx.cpu().numpy()
+        hc_ss = torch.sqrt(hc2ss).cpu().numpy()
+        hc_bg = torch.sqrt(hc2bg).cpu().numpy()
+        sspar = np.array([mt[ssidx[0]], mr[ssidx[1]], rz[ssidx[2]]])
+        return hc_ss, hc_bg, sspar, bgpar.cpu().numpy()
+    hc2ss, hc2bg = cyutils.loudest_hc_from_sorted(number_d, h2fdf, realize, loudest, msort, qsort, zsort,
+                                                  seed=seed, r0=r0, device=True)
+    return torch.sqrt(hc2ss).cpu().numpy(), torch.sqrt(hc2bg).cpu().numpy()

@@ -40,6 +40,8 @@ int holo_abi_version(void);
 const char* holo_last_error(void);
 /* Number of CUDA devices visible (<=0: none). */
 int holo_device_count(void);
+/* Running count of kernels this library has launched in this process (bench.py `gpu_launches`). */
+int64_t holo_launch_count(void);
 
 /* Constants the reference computes once at import with libm (sam_cyutils.pyx:36-42).  The host
  * computes them the same way (libm pow/sqrt) and passes them in, so device code sees identical bits. */
@@ -254,7 +256,11 @@ int holo_ss_bg_hc(const double* number, const double* h2fdf, int Mb, int Qb, int
                   int64_t* ssidx, double* bgpar, double* sspar, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
-int64_t holo_realize_workspace_bytes(int64_t ncell, int F, int R, int nacc);
+/* Scratch bytes for holo_sam_poisson_gwb (kind 0) / holo_ss_bg_hc without (4) or with (5) parameters. */
+#define HOLO_REALIZE_GWB 0
+#define HOLO_REALIZE_SSBG 4
+#define HOLO_REALIZE_SSBG_PAR 5
+int64_t holo_realize_workspace_bytes(int kind, int64_t ncell, int F, int R);
 
 /* poisson_as_needed (gravwaves.py:666-691) / Realizer_SAM bulk draws: out[c] ~ Poisson(lam[c])
  * (floor(Normal) above the threshold).  Flat arrays of n elements. */

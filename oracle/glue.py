@@ -107,14 +107,20 @@ class OracleCosmo:
         return np.vectorize(self._dcom_scalar)(np.asarray(zz, dtype=float))
 
     def tage_to_z(self, age):
-        """Invert age(z) by root finding (cosmopy `tage_to_z`, utils.py:1799,1806)."""
+        """Invert age(z) (cosmopy `tage_to_z`, utils.py:1799,1806): Newton iterations on the
+        quadrature-based `age`, started from a coarse table."""
         age = np.asarray(age, dtype=float)
-        out = np.empty_like(age)
-        flat_in = age.reshape(-1)
-        flat_out = out.reshape(-1)
-        for ii, tt in enumerate(flat_in):
-            flat_out[ii] = sp.optimize.brentq(lambda zz: self._age_scalar(zz) - tt, -0.5, 1.0e4, xtol=1e-14, rtol=1e-14)
-        return out
+        flat = age.reshape(-1)
+        ztab = np.concatenate([[-0.9], -np.logspace(-1, -6, 11), [0.0], np.logspace(-6, 4, 400)])
+        ttab = self.age(ztab)
+        zz = np.interp(flat, ttab[::-1], ztab[::-1])
+        for _ in range(12):
+            resid = self.age(zz) - flat
+            step = resid / self.dtdz(zz)        # dt/dz = -dtdz  =>  z_new = z + resid/dtdz
+            zz = zz + step
+            if np.all(np.abs(step) <= 2e-15 * (1.0 + np.abs(zz))):
+                break
+        return zz.reshape(age.shape)
 
     def comoving_distance_fast(self, zz, npts=20001, zmax=None):
         """Dense-table + cubic-spline version for large arrays (error << 1e-11, checked in tests)."""
@@ -665,27 +671,48 @@ def gws_from_number_grid_integrated_redz(edges, redz, number, realize, dcom_func
 
 # ---- supplied-count helpers: reproduce the seeded reference's draws in its own draw order -------
 
+def _draws_in_order(lam, seed, thresh=1e10):
+    """Draw, in C order of `lam`, exactly what the seeded reference kernels draw: `random_poisson(lam)`
+    or, where ``lam > int(thresh)``, `random_normal(lam, sqrt(lam))` from one PCG64 stream
+    (cyutils.pyx:886-895, 1326-1332).  numpy's Generator methods bind the same C routines."""
+    gen = np.random.Generator(np.random.PCG64(seed))
+    lam = np.ascontiguousarray(lam, dtype=float)
+    big = lam > int(thresh)
+    if not np.any(big):
+        return gen.poisson(lam).astype(float)
+    out = np.empty(lam.size)
+    flat = lam.reshape(-1)
+    bigf = big.reshape(-1)
+    # vectorise the runs between normal-branch elements (the stream is strictly sequential)
+    idx = np.flatnonzero(bigf)
+    beg = 0
+    for ii in idx:
+        if ii > beg:
+            out[beg:ii] = gen.poisson(flat[beg:ii])
+        out[ii] = gen.normal(flat[ii], np.sqrt(flat[ii]))
+        beg = ii + 1
+    if beg < flat.size:
+        out[beg:] = gen.poisson(flat[beg:])
+    return out.reshape(lam.shape)
+
+
 def counts_sam_poisson_gwb(number, nreals, seed, thresh=1e10):
     """Draws of `_sam_poisson_gwb` (cyutils.pyx:881-895, order m,q,z,f then r) -> (R, F, ncell) doubles."""
-    gen = np.random.Generator(np.random.PCG64(seed))
     F = number.shape[-1]
     lam = number.reshape(-1, F)
-    assert not np.any(lam > int(thresh)), "normal-branch cells interleave random_normal; not reproduced here"
-    cnt = gen.poisson(np.repeat(lam.reshape(-1, 1), nreals, axis=1))     # ((cell,f), r) C-order draws
+    cnt = _draws_in_order(np.repeat(lam.reshape(-1, 1), nreals, axis=1), seed, thresh)   # ((cell,f), r)
     cnt = cnt.reshape(lam.shape[0], F, nreals)
-    return np.ascontiguousarray(np.transpose(cnt, (2, 1, 0)).astype(float))
+    return np.ascontiguousarray(np.transpose(cnt, (2, 1, 0)))
 
 
 def counts_loudest(number, order, nreals, seed, thresh=1e10):
     """Draws of the `_loudest_*_from_sorted` kernels (cyutils.pyx:1318-1332: r, then f, then rank order)
     -> (R, F, ncell) doubles indexed by *natural* flat cell index."""
-    gen = np.random.Generator(np.random.PCG64(seed))
     F = number.shape[-1]
     lam = number.reshape(-1, F)
     ncell = lam.shape[0]
-    assert not np.any(lam > int(thresh))
     lam_sorted = lam[order, :].T                                         # (F, ncell) in rank order
-    draws = gen.poisson(np.broadcast_to(lam_sorted, (nreals, F, ncell)))
+    draws = _draws_in_order(np.broadcast_to(lam_sorted, (nreals, F, ncell)), seed, thresh)
     out = np.empty((nreals, F, ncell))
     out[:, :, order] = draws
     return out
@@ -693,12 +720,9 @@ def counts_loudest(number, order, nreals, seed, thresh=1e10):
 
 def counts_ss_bg(number, nreals, seed, thresh=1e10):
     """Draws of `_ss_bg_hc[_and_par]` (cyutils.pyx:981-1001: r, f, then natural m,q,z order)."""
-    gen = np.random.Generator(np.random.PCG64(seed))
     F = number.shape[-1]
     lam = number.reshape(-1, F)
-    assert not np.any(lam > int(thresh))
-    draws = gen.poisson(np.broadcast_to(lam.T, (nreals, F, lam.shape[0])))
-    return draws.astype(float)
+    return _draws_in_order(np.broadcast_to(lam.T, (nreals, F, lam.shape[0])), seed, thresh)
 
 
 # ==================================================================================================

@@ -1,0 +1,40 @@
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+def load_golden(name):
+    with np.load(GOLDEN / f"{name}.npz", allow_pickle=False) as dd:
+        return {kk: dd[kk] for kk in dd.files}
+
+
+@pytest.fixture(scope="session", params=["classic_2pwl", "default_gw", "double_2pwl"])
+def golden(request):
+    return load_golden(request.param)
+
+
+@pytest.fixture(scope="session")
+def golden_classic():
+    return load_golden("classic_2pwl")
+
+
+def rel_err(got, want):
+    """max |got - want| / |want| over elements where want != 0 (and exact agreement of the zero pattern)."""
+    got = np.asarray(got, dtype=float)
+    want = np.asarray(want, dtype=float)
+    sel = (want != 0) & np.isfinite(want)
+    if not np.any(sel):
+        return 0.0
+    return float(np.max(np.abs(got[sel] - want[sel]) / np.abs(want[sel])))

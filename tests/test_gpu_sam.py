@@ -1,0 +1,190 @@
+"""GPU tests of the SAM-level API (density kernel, hardening constructor, `sam.gwb` end to end)
+and of the statistical equivalence of realised spectra with the reference's numpy-RNG path."""
+import numpy as np
+import pytest
+
+from conftest import rel_err, load_golden
+from _stubs import edges_orb, sort_indices
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def holo():
+    import holodeck_b200
+    return holodeck_b200
+
+
+def make_sam(holo, gg, scatter_dex=0.0):
+    """The Semi_Analytic_Model each golden fixture was generated from (tests/golden/make_golden.py)."""
+    from holodeck_b200 import sams, host_relations
+    from holodeck_b200.constants import GYR
+    shape = (gg["mtot"].size, gg["mrat"].size, gg["redz"].size)
+    kind = str(gg["kind"])
+    if kind == "classic":
+        gsmf = sams.GSMF_Schechter(phi0=-2.77, phiz=-0.6, mchar0_log10=11.24, mcharz=0.11, alpha0=-1.21, alphaz=-0.03)
+        gpf = sams.GPF_Power_Law(frac_norm_allq=0.025, malpha=0.0, qgamma=0.0, zbeta=1.0, max_frac=1.0)
+        gmt = sams.GMT_Power_Law(time_norm=0.5*GYR, malpha=0.0, qgamma=-1.0, zbeta=-0.5)
+        mmb = host_relations.MMBulge_KH2013(mamp_log10=8.69, mplaw=1.10, scatter_dex=scatter_dex)
+        return sams.Semi_Analytic_Model(gsmf=gsmf, gpf=gpf, gmt=gmt, mmbulge=mmb, shape=shape)
+    if kind == "default":
+        return sams.Semi_Analytic_Model(shape=shape, mmbulge=host_relations.MMBulge_KH2013(scatter_dex=scatter_dex))
+    if kind == "double":
+        return sams.Semi_Analytic_Model(gsmf=sams.GSMF_Double_Schechter, gpf=sams.GPF_Power_Law, gmt=sams.GMT_Power_Law,
+                                        mmbulge=host_relations.MMBulge_MM2013(scatter_dex=scatter_dex), shape=shape)
+    raise ValueError(kind)
+
+
+def test_static_binary_density(holo, golden):
+    sam = make_sam(holo, golden)
+    assert np.array_equal(sam.mtot, golden["mtot"]) and np.array_equal(sam.redz, golden["redz"])
+    dens = sam.static_binary_density
+    assert dens.shape == sam.shape
+    want = golden["dens"]
+    assert np.array_equal(dens == 0, want == 0)
+    assert rel_err(dens, want) < 1e-10
+    if "gmt_time" in golden:
+        assert rel_err(sam._gmt_time, golden["gmt_time"]) < 1e-12
+        zp, zw = sam._redz_prime, golden["redz_prime"]
+        assert np.array_equal(zp == -1.0, zw == -1.0)
+        assert np.max(np.abs(zp - zw)) < 1e-11
+    else:
+        assert sam._gmt_time is None and sam._redz_prime is None
+    assert sam.static_binary_density is dens   # cached
+
+
+def test_fixed_time_2pl_sam_constructor(holo):
+    from holodeck_b200.constants import GYR, PC
+    gg = load_golden("classic_2pwl")
+    sam = make_sam(holo, gg)
+    hp = gg["hard_params"]
+    hard = holo.hardening.Fixed_Time_2PL_SAM(sam, hp[0], sepa_init=hp[1], rchar=hp[2], gamma_inner=hp[3],
+                                             gamma_outer=hp[4], num_steps=int(hp[5]))
+    assert hard._norm.shape == gg["norm_log10"].shape
+    diff = np.abs(np.log10(hard._norm) - gg["norm_log10"])
+    assert np.sum(diff > 1e-10) <= 1 and diff.max() < 2e-3
+    # dadt through the vectorised native function vs the closed form
+    sepa = 10.0 * PC
+    dadt = hard.dadt(sam.mtot[:, None], sam.mrat[None, :], sepa)
+    xx = sepa / hp[2]
+    want = -hard._norm * np.power(1.0 + xx, -hp[4] + hp[3]) / np.power(xx, hp[3] - 1) + \
+        holo.hardening.Hard_GW.dadt(sam.mtot[:, None], sam.mrat[None, :], sepa) * (6.6742999e-08 / holo.constants.NWTG)**3
+    assert rel_err(dadt, want) < 1e-8
+    assert 3.0 * GYR == hp[0]
+
+
+def test_sam_gwb_end_to_end_matches_oracle_chain(holo):
+    """sam.gwb on the GPU vs the oracle chain on the same SAM: deterministic intermediates to 1e-10,
+    expectation-value spectrum to 1e-10, realised spectrum consistent with it."""
+    gg = load_golden("classic_2pwl")
+    sam = make_sam(holo, gg)
+    hp = gg["hard_params"]
+    hard = holo.hardening.Fixed_Time_2PL_SAM(sam, hp[0], sepa_init=hp[1], rchar=hp[2], gamma_inner=hp[3],
+                                             gamma_outer=hp[4], num_steps=int(hp[5]))
+    fobs_edges = gg["fobs_edges"]
+    grid, dnum, redz_final = sam.dynamic_binary_number_at_fobs(hard, gg["fobs_cents"] / 2.0)
+    assert np.sum((redz_final == -1) != (gg["redz_final"] == -1)) == 0
+    assert rel_err(redz_final, gg["redz_final"]) < 1e-9
+    assert rel_err(dnum, gg["diff_num"]) < 1e-9
+    R, L = 64, 4
+    hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=1)
+    F = fobs_edges.size - 1
+    assert hc_ss.shape == (F, R, L) and hc_bg.shape == (F, R)
+    assert np.all(np.isfinite(hc_ss)) and np.all(hc_bg > 0)
+    # loudest sources are sorted by rank at f0, so at the first frequency they are non-increasing
+    assert np.all(np.diff(hc_ss[0], axis=-1) <= 0)
+    tot = hc_bg**2 + np.sum(hc_ss**2, axis=-1)
+    # the realised total scatters around the expectation; medians agree to within the bin's shot noise
+    expect = gg["hc2_expect"]
+    ratio = np.median(tot, axis=1) / expect
+    assert np.all((ratio > 0.2) & (ratio < 5.0)), ratio
+    out = sam.gwb(fobs_edges, hard, realize=8, loudest=2, params=True, seed=2)
+    assert out[2].shape == (4, F, 8, 2) and out[3].shape == (7, F, 8)
+    assert np.all((out[2][3] > 0) | (out[2][3] == -1) | (out[2][3] == 0))
+    with pytest.raises(ValueError):
+        sam.gwb(fobs_edges, object(), realize=2)
+    hc = sam.gwb_new(fobs_edges, hard, realize=16, seed=3)
+    assert hc.shape == (F, 16)
+
+
+def test_default_sam_hard_gw_config0(holo):
+    """BASELINE config 0: default Semi_Analytic_Model(shape=30) with Hard_GW, 20 PTA frequencies, realize=10."""
+    from holodeck_b200 import utils, host_relations
+    from holodeck_b200.constants import YR
+    sam = holo.sams.Semi_Analytic_Model(shape=30, mmbulge=host_relations.MMBulge_KH2013(scatter_dex=0.0))
+    fobs_cents, fobs_edges = utils.pta_freqs(10.0*YR, 20)
+    hc_ss, hc_bg = sam.gwb(fobs_edges, holo.hardening.Hard_GW(), realize=10, seed=5)
+    assert hc_ss.shape == (20, 10, 1) and hc_bg.shape == (20, 10)
+    assert np.all(hc_bg > 0) and np.all(np.isfinite(hc_bg))
+    # a GW-driven background falls as ~f^-2/3
+    med = np.median(hc_bg, axis=1)
+    slope = np.polyfit(np.log(fobs_cents[:8]), np.log(med[:8]), 1)[0]
+    assert -1.2 < slope < -0.4, slope
+    ideal = sam.gwb_ideal(fobs_cents)
+    assert np.all(np.abs(np.log10(med[:5] / ideal[:5])) < 0.5)
+
+
+def _quantiles(arr):
+    return np.percentile(arr, [5, 50, 95], axis=1)
+
+
+def test_realised_gwb_statistically_matches_reference(holo):
+    """Per-frequency median and 5-95% quantiles of hc from the Philox/CUDA sampler vs the reference's
+    numpy-PCG64 sampler agree within Monte-Carlo error (two independent R=1500 samples)."""
+    from holodeck_b200 import cyutils
+    from oracle import glue
+    gg = load_golden("classic_2pwl")
+    R = 1500
+    cy, _, _ = glue.ref()
+    cy.ORACLE_SEED = 2024
+    ref = np.sqrt(np.asarray(cy.sam_poisson_gwb(gg["number"], gg["h2fdf"], R)))
+    cy.ORACLE_SEED = None
+    got = np.sqrt(cyutils.sam_poisson_gwb(gg["number"], gg["h2fdf"], R, seed=99))
+    qr, qg = _quantiles(ref), _quantiles(got)
+    # bootstrap the MC error of each quantile from the reference sample
+    rng = np.random.default_rng(0)
+    boots = np.array([_quantiles(ref[:, rng.integers(0, R, R)]) for _ in range(200)])
+    sig = boots.std(axis=0) * np.sqrt(2.0) + 1e-3 * qr
+    assert np.all(np.abs(qg - qr) < 5.0 * sig), (np.abs(qg - qr) / sig).max()
+    # means are unbiased: sum over realizations of hc^2 matches the expectation value
+    mean_got = np.mean(got**2, axis=1)
+    err = np.std(got**2, axis=1) / np.sqrt(R)
+    assert np.all(np.abs(mean_got - gg["hc2_expect"]) < 6 * err + 1e-6 * gg["hc2_expect"])
+
+
+def test_loudest_statistically_matches_reference(holo):
+    from holodeck_b200 import cyutils
+    from oracle import glue
+    gg = load_golden("classic_2pwl")
+    R, L = 1200, 3
+    ms, qs, zs = sort_indices(gg)
+    cy, _, _ = glue.ref()
+    cy.ORACLE_SEED = 4242
+    r_ss, r_bg = [np.sqrt(np.asarray(vv)) for vv in cy.loudest_hc_from_sorted(gg["number"], gg["h2fdf"], R, L, ms, qs, zs)]
+    cy.ORACLE_SEED = None
+    g_ss, g_bg = [np.sqrt(vv) for vv in cyutils.loudest_hc_from_sorted(gg["number"], gg["h2fdf"], R, L, ms, qs, zs, seed=17)]
+    rng = np.random.default_rng(1)
+    for ref, got in ((r_bg, g_bg), (r_ss[..., 0], g_ss[..., 0]), (r_ss[..., L-1], g_ss[..., L-1])):
+        qr, qg = _quantiles(ref), _quantiles(got)
+        boots = np.array([_quantiles(ref[:, rng.integers(0, R, R)]) for _ in range(200)])
+        sig = boots.std(axis=0) * np.sqrt(2.0) + 1e-3 * np.abs(qr) + 1e-30
+        assert np.all(np.abs(qg - qr) < 5.0 * sig), (np.abs(qg - qr) / sig).max()
+
+
+def test_poisson_as_needed_moments(holo):
+    from holodeck_b200 import gravwaves
+    lam = np.repeat(np.array([0.0, 1e-3, 0.7, 5.0, 9.99, 10.0, 37.5, 1e3, 3e6, 5e10]), 40000).reshape(10, 40000)
+    out = gravwaves.poisson_as_needed(lam, seed=11)
+    assert out.shape == lam.shape and np.all(out == np.floor(out)) and np.all(out >= 0)
+    mean = out.mean(axis=1)
+    var = out.var(axis=1)
+    l0 = lam[:, 0]
+    assert mean[0] == 0
+    sem = np.sqrt(np.maximum(l0, 1e-12) / lam.shape[1])
+    assert np.all(np.abs(mean - l0)[:-1] < 5 * sem[:-1] + 1e-12)
+    assert np.all(np.abs(var[2:-1] / l0[2:-1] - 1.0) < 0.05)
+    # normal branch above the threshold is floored: mean ~ lam - 0.5
+    assert abs(mean[-1] - (l0[-1] - 0.5)) < 5 * sem[-1]
+    # P(n >= 1) for tiny lam is resolved (64-bit uniform)
+    tiny = gravwaves.poisson_as_needed(np.full(4_000_000, 2.5e-6), seed=12)
+    assert abs(tiny.sum() - 10.0) < 5 * np.sqrt(10.0)
