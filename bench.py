@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: cell-realizations/s of `sam.gwb` on the (91x81x101x40, realize=1000) grid.
+
+Contract (see the task statement):  ``python bench.py --gpus N --steps K --warmup W [--impl reference]``
+prints ONE JSON line on rank 0.  For N>1 it is launched under torchrun (one rank per GPU).
+
+Step (this arm)   one full pass of the hot path for BASELINE.json configs[1]: a fresh
+                  ``Semi_Analytic_Model`` (PS_Classic defaults, M-Mbulge scatter off -- the scatter is
+                  the host-scipy "next" row N1 and is not part of the path) -> ``Fixed_Time_2PL_SAM``
+                  (K1a) -> ``sam.gwb(fobs_edges, hard, realize=R, loudest=L)`` (K0, K1b, K2+K2b, rank sort,
+                  K4).  `value` keeps every array on the device; `e2e` is the same call through the public
+                  numpy API (host edge arrays in, hc_ss / hc_bg numpy out, PCIe copies inside the timing).
+N > 1             realizations shard: every rank runs R realizations (global realization index
+                  r0 = rank*R, so the union is one R*N-realization run), then the per-rank hc arrays are
+                  all-gathered over NCCL.  Weak scaling; value = N*cells*R / max-over-ranks time.
+--impl reference  the reference's own CPU path (compiled reference Cython from oracle/_ref driven by
+                  oracle/chain.py), all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "cell-realizations/s for sam.gwb (91x81x101x40, realize=1000)"
+UNIT = "cell-realizations/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shape", type=int, nargs=3, default=[91, 81, 101], help="(debug) grid edges M Q Z")
+    ap.add_argument("--nfreqs", type=int, default=40)
+    ap.add_argument("--realize", type=int, default=1000)
+    ap.add_argument("--loudest", type=int, default=1, help="sam.gwb default")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-reals", type=int, default=2, help="realizations in the bounded CPU sample")
+    return ap.parse_args()
+
+
+def peaks():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        dd = json.loads(path.read_text())
+        return dict(hbm_gbs=float(dd["hbm_gbs"]), sm_max_mhz=float(dd.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+# ==================================================================================================
+# clocks sampler (nvidia-smi, recipe of /opt/skills/guides/B200_PROFILING.md)
+# ==================================================================================================
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            parts = [pp.strip() for pp in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                clk, cmax = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            if t0 <= ts <= t1 + 0.1:
+                sm.append(clk)
+                smax.append(cmax)
+                for nn, vv in zip(names, parts[5:9]):
+                    if vv.lower().startswith("active"):
+                        reasons.add(nn)
+        if not sm:   # timed region shorter than the sampling period: use everything we saw
+            for ts, line in self.lines:
+                parts = [pp.strip() for pp in line.split(",")]
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ==================================================================================================
+# reference arm / CPU baseline
+# ==================================================================================================
+
+_STATE = None   # reference grids, inherited copy-on-write by forked workers (never pickled)
+
+
+def _cpu_worker(args):
+    """One process = one independent run of the reference's realised stage on its own view of the grids."""
+    nreals, loudest, seed = args
+    from oracle import chain
+    _, _, dt = chain.reference_realize(_STATE, nreals, loudest, seed=seed)
+    return dt
+
+
+def cpu_reference(args, nproc, nreals_each, state=None, tdet=None):
+    """Bounded sample of the reference CPU path.  Returns (cell_real_per_s, info dict, state, tdet)."""
+    from oracle import chain
+    wl = chain.classic_workload(shape=tuple(args.shape), nfreqs=args.nfreqs)
+    if state is None:
+        state, tdet = chain.reference_deterministic(wl)
+    global _STATE
+    _STATE = state
+    ncell = int(np.prod(state["number"].shape))
+    t_det = float(sum(tdet.values()))
+    if nproc <= 1:
+        t0 = time.perf_counter()
+        _cpu_worker((nreals_each, args.loudest, 1))
+        wall = time.perf_counter() - t0
+    else:
+        import multiprocessing as mp
+        ctx = mp.get_context("fork")
+        with ctx.Pool(nproc) as pool:
+            pool.map(_cpu_worker, [(0, args.loudest, 0)] * nproc)     # spin the workers up (imports) untimed
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(nreals_each, args.loudest, 1 + ii) for ii in range(nproc)], chunksize=1)
+            wall = time.perf_counter() - t0
+    # the realised stage is exactly linear in R (cyutils.pyx:1318); nproc processes each did nreals_each
+    # realizations concurrently in `wall` seconds -> seconds per realization per process = wall/nreals_each
+    t_real = wall / nreals_each
+    # a full job per process: deterministic stages once + R realizations; nproc jobs run side by side
+    t_job = t_det + args.realize * t_real
+    value = nproc * ncell * args.realize / t_job
+    info = dict(t_deterministic_s=round(t_det, 3), t_per_realization_s=round(t_real, 4), stage_s={kk: round(vv, 3) for kk, vv in tdet.items()})
+    return value, info, state, tdet
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nproc = os.cpu_count() or 1
+    state, tdet = None, None
+    vals = []
+    t_begin = time.perf_counter()
+    for ii in range(args.warmup + args.steps):
+        val, info, state, tdet = cpu_reference(args, nproc, 1, state, tdet)
+        if ii >= args.warmup:
+            vals.append(val)
+    wall = time.perf_counter() - t_begin
+    value = float(np.mean(vals))
+    ncell = int(np.prod(state["number"].shape))
+    sample = (f"{nproc} processes x 1 realization of loudest_hc_from_sorted (L={args.loudest}) on the full "
+              f"{'x'.join(map(str, state['number'].shape))} grid per step, extrapolated linearly to R={args.realize}; "
+              f"deterministic stages (density, 2PL norm, dbn, integrate, strain+argsort) timed once: {info['t_deterministic_s']} s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * ncell * args.realize * nproc / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample, **info},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": round(wall, 1),
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    M, Q, Z = args.shape
+    return {"workload": f"sam.gwb PS_Classic (scatter off) + Fixed_Time_2PL_SAM(3 Gyr), grid {M}x{Q}x{Z}x{args.nfreqs}, "
+                        f"realize={args.realize}, loudest={args.loudest}",
+            "grid": [M, Q, Z, args.nfreqs], "realize": args.realize, "loudest": args.loudest,
+            "parallelism": f"realization-sharded x{args.gpus}",
+            "cache": "inputs larger than L2 (2 x 238 MB grids re-streamed every step; no explicit flush)"}
+
+
+# ==================================================================================================
+# B200 arm
+# ==================================================================================================
+
+def make_models(args):
+    """Fresh SAM + hardening for configs[1] (librarian/param_spaces_classic.py:13-89, scatter off)."""
+    import holodeck_b200 as holo
+    from holodeck_b200 import sams, host_relations
+    from holodeck_b200.constants import GYR, PC
+    gsmf = sams.GSMF_Schechter(phi0=-2.77, phiz=-0.6, mchar0_log10=11.24, mcharz=0.11, alpha0=-1.21, alphaz=-0.03)
+    gpf = sams.GPF_Power_Law(frac_norm_allq=0.025, malpha=0.0, qgamma=0.0, zbeta=1.0, max_frac=1.0)
+    gmt = sams.GMT_Power_Law(time_norm=0.5*GYR, malpha=0.0, qgamma=-1.0, zbeta=-0.5)
+    mmb = host_relations.MMBulge_KH2013(mamp_log10=8.69, mplaw=1.10, scatter_dex=0.0)
+    sam = sams.Semi_Analytic_Model(gsmf=gsmf, gpf=gpf, gmt=gmt, mmbulge=mmb, shape=tuple(args.shape))
+    hard = holo.hardening.Fixed_Time_2PL_SAM(sam, 3.0*GYR, sepa_init=1e4*PC, rchar=100.0*PC, gamma_inner=-1.0,
+                                             gamma_outer=+2.5)
+    return sam, hard
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import holodeck_b200 as holo   # noqa: F401
+    from holodeck_b200 import _lib, utils
+    from holodeck_b200.constants import YR
+    lib = _lib.require_gpu()
+
+    fobs_cents, fobs_edges = utils.pta_freqs(16.03*YR, args.nfreqs)
+    R, L = args.realize, args.loudest
+    r0 = rank * R
+    M, Q, Z = args.shape
+    ncell = (M - 1) * (Q - 1) * (Z - 1) * args.nfreqs
+    seed = 12345
+
+    def gather(tt):
+        if world == 1:
+            return tt
+        outs = [torch.empty_like(tt) for _ in range(world)]
+        dist.all_gather(outs, tt)
+        return torch.cat(outs, dim=1)
+
+    def step_device():
+        sam, hard = make_models(args)
+        hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0, device=True)
+        return gather(hc_ss), gather(hc_bg)
+
+    def step_e2e():
+        sam, hard = make_models(args)
+        if world == 1:
+            return sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0)
+        hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0, device=True)
+        return _lib.to_host(gather(hc_ss)), _lib.to_host(gather(hc_bg))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, nsteps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(nsteps):
+            out = fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out, t0, t1
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    n_launch0 = lib.holo_launch_count()
+    ms_total, out, t0, t1 = timed(step_device, args.steps)
+    n_launch = lib.holo_launch_count() - n_launch0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    value = world * ncell * R * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public numpy API
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    _lib.TRAFFIC["h2d"] = _lib.TRAFFIC["d2h"] = 0
+    ms_e2e, out_e2e, _, _ = timed(step_e2e, args.steps)
+    h2d = _lib.TRAFFIC["h2d"] // args.steps
+    d2h = _lib.TRAFFIC["d2h"] // args.steps
+    e2e_value = world * ncell * R * args.steps / (ms_e2e * 1e-3)
+    assert out_e2e[0].shape == (args.nfreqs, R * world, L) and out_e2e[1].shape == (args.nfreqs, R * world)
+    assert np.all(np.isfinite(out_e2e[1])) and np.all(out_e2e[1] > 0)
+
+    # ---- per-stage device times (CUDA events on the launching stream), one extra profiled pass
+    stages = stage_times(args, fobs_edges, R, L, seed, r0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    nedge = M * Q * Z * args.nfreqs
+    alg_bytes = {   # algorithmic bytes per launch (DESIGN.md "Kernels and rooflines")
+        "density": 3 * M * Q * Z * 8,
+        "norm_2pwl": 3 * M * Q * 8,
+        "dbn_2pwl": 2 * nedge * 8 + 2 * M * Q * Z * 8,
+        "integrate_strain": 2 * nedge * 8 + 2 * ncell * 8,
+        "loudest_draw": 2 * ncell * 8,
+    }
+    dom = max((kk for kk in stages if kk in alg_bytes), key=lambda kk: stages[kk])
+    ach = alg_bytes[dom] / (stages[dom] * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "ms": stages[dom], "algorithmic_bytes": alg_bytes[dom]}
+    per_kernel = {}
+    for kk, bb in alg_bytes.items():
+        if kk in stages and stages[kk] > 0:
+            gbs = bb / (stages[kk] * 1e-3) / 1e9
+            per_kernel[kk] = {"ms": round(stages[kk], 4), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / pk["hbm_gbs"], 4)}
+    # the draw kernel is instruction-issue bound, not HBM bound: nominal 25 thread-instructions per
+    # cell-realization against 148 SM x 4 schedulers x 32 lanes x clock
+    clk = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
+    issue_peak = 148 * 4 * 32 * clk * 1e6
+    if "loudest_draw" in stages:
+        rate = ncell * R / (stages["loudest_draw"] * 1e-3)
+        per_kernel["loudest_draw"].update({"cell_real_per_s": rate, "issue_frac_nominal25": round(rate * 25 / issue_peak, 4)})
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(n_launch),
+        "roofline": roofline,
+        "stages_ms": {kk: round(vv, 4) for kk, vv in stages.items()},
+        "kernels": per_kernel,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            val, info, _, _ = cpu_reference(args, 1, args.cpu_reals)
+            line["cpu_baseline"] = {
+                "value": val, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": (f"reference chain on the same workload: deterministic stages once + {args.cpu_reals} realizations of "
+                           f"loudest_hc_from_sorted (compiled reference, oracle/_ref), extrapolated linearly to R={R}"),
+                **info}
+        except Exception as err:   # the oracle did not travel: say so instead of inventing a number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {err}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def stage_times(args, fobs_edges, R, L, seed, r0):
+    """Device time of each stage of one step, CUDA events on the launching (torch current) stream."""
+    import ctypes as C
+    import torch
+    from holodeck_b200 import _lib, gravwaves, single_sources, cosmo, utils
+    from holodeck_b200.sams import sam_cyutils
+    lib = _lib.load()
+    res = {}
+
+    def ev():
+        ee = torch.cuda.Event(enable_timing=True)
+        ee.record()
+        return ee
+
+    best = {}
+    for rep in range(3):
+        torch.cuda.synchronize()
+        marks = [("start", ev())]
+        sam, hard = make_models(args)     # K1a runs in the hardening constructor; density is lazy
+        marks.append(("norm_2pwl", ev()))
+        sam._static_binary_density_device()
+        marks.append(("density", ev()))
+        fobs_gw_cents = utils.midpoints(fobs_edges)
+        redz_final, diff_num = sam_cyutils.dynamic_binary_number_at_fobs(fobs_gw_cents / 2.0, sam, hard, cosmo, device=True)
+        marks.append(("dbn_2pwl", ev()))
+        edges = [sam.mtot, sam.mrat, sam.redz, fobs_edges / 2.0]
+        strain = gravwaves._char_strain_sq(edges, redz_final, params=False, dnum=diff_num)
+        marks.append(("integrate_strain", ev()))
+        lib.holo_set_profiling(1)
+        single_sources.ss_gws_redz(edges, redz_final, strain["number"], realize=R, loudest=L, seed=seed, r0=r0,
+                                   device=True, _precomputed=strain)
+        lib.holo_set_profiling(0)
+        marks.append(("ss_gws_redz_total", ev()))
+        torch.cuda.synchronize()
+        prof = (C.c_double * 8)()
+        nn = lib.holo_get_profile(prof, 8)
+        cur = {marks[ii][0]: marks[ii - 1][1].elapsed_time(marks[ii][1]) for ii in range(1, len(marks))}
+        if nn >= 4:
+            cur.update({"loudest_head_prep": prof[0], "loudest_draw": prof[1], "loudest_resolve": prof[2], "loudest_final": prof[3]})
+            cur["rank_sort_and_glue"] = cur["ss_gws_redz_total"] - sum(prof[ii] for ii in range(4))
+        for kk, vv in cur.items():
+            best[kk] = min(best.get(kk, 1e30), vv)
+    res.update(best)
+    return res
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

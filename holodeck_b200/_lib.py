@@ -137,6 +137,8 @@ SIGNATURES = {
     "holo_last_error": [],
     "holo_device_count": [],
     "holo_launch_count": [],
+    "holo_set_profiling": [_I],
+    "holo_get_profile": [_P, _I],
     "holo_sam_density": [_P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(SamParams), _P, _P, _P, _P],
     "holo_zero_stalled": [_P, _P, _L, _P],
     "holo_find_2pwl_hardening_norm": [CyConsts, _D, _P, _P, _I, _D, _D, _D, _D, _I, _P, _P],
@@ -238,16 +240,28 @@ def to_dev(arr, dtype=None, dev=None):
     if isinstance(arr, torch.Tensor):
         tt = arr
         if not tt.is_cuda:
+            TRAFFIC["h2d"] += tt.numel() * tt.element_size()
             tt = tt.to(device(dev), non_blocking=True)
         return tt.to(dtype).contiguous()
     arr = np.ascontiguousarray(arr)
     tt = torch.from_numpy(arr)
+    TRAFFIC["h2d"] += arr.nbytes
     return tt.to(device=device(dev), dtype=dtype, non_blocking=True).contiguous()
 
 
 def empty(shape, dtype=None, dev=None):
     import torch
     return torch.empty(shape, dtype=torch.float64 if dtype is None else dtype, device=device(dev))
+
+
+#: bytes moved across PCIe by the shims (bench.py reads these for `h2d_bytes_per_step` / `d2h_bytes_per_step`)
+TRAFFIC = {"h2d": 0, "d2h": 0}
+
+
+def to_host(tensor):
+    """CUDA tensor -> numpy array (counted device-to-host copy)."""
+    TRAFFIC["d2h"] += tensor.numel() * tensor.element_size()
+    return tensor.cpu().numpy()
 
 
 def ptr(tensor):

@@ -17,11 +17,27 @@ void set_error(const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static bool g_profiling = false;
+static double g_profile[8];
+static int g_nprofile = 0;
+bool profiling_on() { return g_profiling; }
+void store_profile(const double* ms, int n) {
+    g_nprofile = n < 8 ? n : 8;
+    for (int i = 0; i < g_nprofile; ++i) g_profile[i] = ms[i];
+}
 }  // namespace holo
 
 extern "C" {
 
 int64_t holo_launch_count(void) { return (int64_t)holo::g_launches.load(); }
+
+void holo_set_profiling(int on) { holo::g_profiling = (on != 0); }
+
+int holo_get_profile(double* ms, int n) {
+    int m = holo::g_nprofile < n ? holo::g_nprofile : n;
+    for (int i = 0; i < m; ++i) ms[i] = holo::g_profile[i];
+    return m;
+}
 
 int holo_abi_version(void) { return HOLO_ABI_VERSION; }
 

@@ -7,6 +7,36 @@
 namespace holo {
 void set_error(const char* fmt, ...);
 void count_launches(int n);
+bool profiling_on();
+void store_profile(const double* ms, int n);
+
+// Records up to 8 events on a stream; `finish()` synchronises and stores the gaps as the profile.
+struct StageTimer {
+    cudaEvent_t ev[8];
+    int n = 0;
+    bool on;
+    cudaStream_t st;
+    explicit StageTimer(cudaStream_t s) : on(profiling_on()), st(s) {}
+    void mark() {
+        if (!on || n >= 8) return;
+        cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], st);
+        ++n;
+    }
+    void finish() {
+        if (!on || n < 2) return;
+        cudaEventSynchronize(ev[n - 1]);
+        double ms[8];
+        for (int i = 0; i + 1 < n; ++i) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+            ms[i] = t;
+        }
+        store_profile(ms, n - 1);
+        for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+        n = 0;
+    }
+};
 }
 
 extern "C" int holo_check_launch(const char* who);

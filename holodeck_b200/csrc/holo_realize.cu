@@ -686,12 +686,17 @@ int holo_sam_poisson_gwb(const double* number, const double* h2fdf, int64_t ncel
     ra.ncell = ncell; ra.chunk = p.chunk; ra.Qb = 1; ra.Zb = 1; ra.F = F; ra.R = R; ra.cap = 0;
     ra.r0 = r0; ra.k0 = (uint32_t)seed; ra.k1 = (uint32_t)(seed >> 32);
     ra.thresh = (double)(int64_t)normal_threshold;                       // `long thresh`, pyx:855, 863
+    StageTimer timer(st);
+    timer.mark();
     int rc = launch_realize<V_GWB>(ra, p, st);
     if (rc) return rc;
+    timer.mark();
     FinalArgs fa{};
     fa.partial = l.partial; fa.out0 = gwb; fa.nchunk = p.nchunk; fa.Qb = 1; fa.Zb = 1; fa.F = F; fa.R = R;
     int64_t nfr = (int64_t)F * R;
     final_kernel<V_GWB><<<(int)((nfr + 255) / 256), 256, 0, st>>>(fa); holo::count_launches(1);
+    timer.mark();
+    timer.finish();
     return holo_check_launch("holo_sam_poisson_gwb");
 }
 
@@ -729,6 +734,8 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     if (v == V_LOUD_PAR_REDZ) HOLO_CUDA(cudaMemsetAsync(g->sspar, 0, sizeof(double) * 4 * nfr * L, st));
 
     // ---- head preparation
+    StageTimer timer(st);
+    timer.mark();
     rank_inverse_kernel<<<(int)((ncell + 255) / 256 > 4736 ? 4736 : (ncell + 255) / 256), 256, 0, st>>>(
         g->order, ncell, l.rank); holo::count_launches(1);
     int nblk = (int)((ncell + HEAD_ROWS - 1) / HEAD_ROWS);
@@ -739,6 +746,7 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     int rc = holo_check_launch("holo_loudest: head preparation");
     if (rc) return rc;
 
+    timer.mark();
     // ---- draws
     RealizeArgs ra{};
     ra.number = g->number; ra.h2fdf = g->h2fdf; ra.rank = l.rank; ra.kf = l.kf;
@@ -753,6 +761,7 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     else rc = launch_realize<V_LOUD_PAR_REDZ>(ra, p, st);
     if (rc) return rc;
 
+    timer.mark();
     // ---- resolve the head, then reduce
     ResolveArgs rs{};
     rs.events = l.events; rs.evcount = l.evcount; rs.kf = l.kf; rs.h2fdf = g->h2fdf;
@@ -774,6 +783,7 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     }
     rc = holo_check_launch("holo_loudest: resolve");
     if (rc) return rc;
+    timer.mark();
 
     FinalArgs fa{};
     fa.partial = l.partial; fa.rem = l.rem; fa.out0 = g->hc2bg; fa.bgpar = g->bgpar;
@@ -785,6 +795,8 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     holo::count_launches(1);
     rc = holo_check_launch("holo_loudest: final");
     if (rc) return rc;
+    timer.mark();
+    timer.finish();
 
     int32_t flags[4] = {0, 0, 0, 0};
     HOLO_CUDA(cudaMemcpyAsync(flags, l.flags, sizeof(flags), cudaMemcpyDeviceToHost, st));

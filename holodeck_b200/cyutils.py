@@ -42,7 +42,7 @@ def _workspace(nbytes):
 
 
 def _out(tensor, device):
-    return tensor if device else tensor.cpu().numpy()
+    return tensor if device else _lib.to_host(tensor)
 
 
 def _counts(counts, R, F, ncell):

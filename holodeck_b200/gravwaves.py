@@ -92,13 +92,13 @@ def char_strain_sq_from_bin_edges_redz(edges, redz, device=None):
     """
     on_dev = _lib.is_device_array(redz) if device is None else device
     out = _char_strain_sq(edges, redz)["h2fdf"]
-    return out if on_dev else out.cpu().numpy()
+    return out if on_dev else _lib.to_host(out)
 
 
 def char_strain_sq_from_bin_edges(edges, device=False):
     """As above but every bin sits at its initial (bin-centre) redshift (``gravwaves.py:760-783``)."""
     out = _char_strain_sq(edges, None)["h2fdf"]
-    return out if device else out.cpu().numpy()
+    return out if device else _lib.to_host(out)
 
 
 def poisson_as_needed(values, thresh=1e10, *, seed=None, device=None):
@@ -111,7 +111,7 @@ def poisson_as_needed(values, thresh=1e10, *, seed=None, device=None):
     rc = lib.holo_poisson_as_needed(_lib.ptr(lam), lam.numel(), _seed(seed), 0, float(thresh), _lib.ptr(out),
                                     _lib.stream())
     _lib.check(rc, "poisson_as_needed")
-    return out if on_dev else out.cpu().numpy()
+    return out if on_dev else _lib.to_host(out)
 
 
 def _expectation(number, hc2):
@@ -154,7 +154,7 @@ def _gws_from_hc2(hc2, number, realize, sum, seed, r0, on_dev):
         log.error(err)
         raise ValueError(err)
     hc = torch.sqrt(hc2)
-    return hc if on_dev else hc.cpu().numpy()
+    return hc if on_dev else _lib.to_host(hc)
 
 
 def _gws_from_number_grid_integrated_redz(edges, redz, number, realize, sum=True, *, seed=None, r0=0, device=None):

@@ -14,7 +14,7 @@ import abc
 import numpy as np
 
 import holodeck_b200 as holo
-from holodeck_b200 import utils
+from holodeck_b200 import utils, _lib
 from holodeck_b200.constants import GYR, PC
 
 
@@ -114,7 +114,7 @@ class Fixed_Time_2PL_SAM(_Hardening):
     def _norm(self):
         """(M, Q) hardening-rate normalisation [cm/s] (numpy; ``hardening.py:1416``)."""
         if self._norm_host is None:
-            self._norm_host = self._norm_dev.cpu().numpy()
+            self._norm_host = _lib.to_host(self._norm_dev)
         return self._norm_host
 
     def _norm_device(self):

@@ -250,7 +250,7 @@ class Semi_Analytic_Model:
         if scatter > 0.0:
             log.info(f"Adding MMbulge scatter ({scatter:.4e})")
             dur = datetime.now()
-            dens_host = dens.cpu().numpy()
+            dens_host = _lib.to_host(dens)
             mass_bef = self._integrated_binary_density(dens_host, sum=True)
             self._dens_bef = np.copy(dens_host)
             dens_host = add_scatter_to_masses(self.mtot, self.mrat, dens_host, scatter, log=log)
@@ -283,7 +283,7 @@ class Semi_Analytic_Model:
         Cached after the first access, like the reference (``sam.py:280-398``).
         """
         if self._density_host is None:
-            self._density_host = self._static_binary_density_device().cpu().numpy()
+            self._density_host = _lib.to_host(self._static_binary_density_device())
         return self._density_host
 
     @property
@@ -300,14 +300,14 @@ class Semi_Analytic_Model:
     def _gmt_time(self):
         """(M, Q, Z) galaxy-merger time [s]; `None` until the density exists or if there is no GMT."""
         if (self._gmt_time_host is None) and (self._gmt_time_dev is not None):
-            self._gmt_time_host = self._gmt_time_dev.cpu().numpy()
+            self._gmt_time_host = _lib.to_host(self._gmt_time_dev)
         return self._gmt_time_host
 
     @property
     def _redz_prime(self):
         """(M, Q, Z) redshift after the galaxy merger (-1 if after z=0); `None` as for `_gmt_time`."""
         if (self._redz_prime_host is None) and (self._redz_prime_dev is not None):
-            self._redz_prime_host = self._redz_prime_dev.cpu().numpy()
+            self._redz_prime_host = _lib.to_host(self._redz_prime_dev)
         return self._redz_prime_host
 
     def _integrated_binary_density(self, ndens=None, sum=True):
@@ -384,7 +384,7 @@ class Semi_Analytic_Model:
         mr = self.mrat[np.newaxis, :, np.newaxis]
         return gravwaves.gwb_ideal(fobs_gw, ndens, mt, mr, rz, dlog10=True, sum=sum)
 
-    def gwb(self, fobs_gw_edges, hard=None, realize=100, loudest=1, params=False, *, seed=None, r0=0):
+    def gwb(self, fobs_gw_edges, hard=None, realize=100, loudest=1, params=False, *, seed=None, r0=0, device=False):
         """Calculate the (smooth/semi-analytic) GWB and CWs at the given observed GW-frequencies.
 
         Parameters
@@ -399,7 +399,7 @@ class Semi_Analytic_Model:
             Number of loudest single sources to distinguish from the background.
         params : bool
             Whether or not to return astrophysical parameters of the binaries.
-        seed, r0 : keyword-only additions (see ``holodeck_b200.cyutils``).
+        seed, r0, device : keyword-only additions (see ``holodeck_b200.cyutils``); ``device=True`` returns CUDA tensors.
 
         Returns
         -------
@@ -425,7 +425,7 @@ class Semi_Analytic_Model:
         edges, redz_final, strain = self._number_and_strain(fobs_gw_edges, hard, params=bool(params))
         number = strain["number"]
         ret_vals = single_sources.ss_gws_redz(edges, redz_final, number, realize=realize, loudest=loudest,
-                                              params=params, seed=seed, r0=r0, _precomputed=strain)
+                                              params=params, seed=seed, r0=r0, device=device, _precomputed=strain)
         hc_ss = ret_vals[0]
         hc_bg = ret_vals[1]
         if params:

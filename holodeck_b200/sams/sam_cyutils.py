@@ -23,7 +23,7 @@ def _out(tensor, like_device):
     """Return `tensor` as numpy unless the caller passed device arrays."""
     if like_device:
         return tensor
-    return tensor.cpu().numpy()
+    return _lib.to_host(tensor)
 
 
 def hard_gw(mtot, mrat, sepa):
@@ -90,7 +90,7 @@ def hard_func_2pwl_gw(mtot, mrat, sepa, norm, rchar, gamma_inner, gamma_outer):
     rc = lib.holo_hard_func_2pwl_gw(_lib.cy_consts(), _lib.ptr(mtot), _lib.ptr(mrat), _lib.ptr(sepa), _lib.ptr(norm),
                                     rchar, gamma_inner, gamma_outer, mtot.numel(), _lib.ptr(dadt), _lib.stream())
     _lib.check(rc, "hard_func_2pwl_gw")
-    return dadt.cpu().numpy().reshape(shape)
+    return _lib.to_host(dadt).reshape(shape)
 
 
 def find_2pwl_hardening_norm(time, mtot, mrat, sepa_init, rchar, gamma_inner, gamma_outer, nsteps, device=False):
@@ -124,7 +124,7 @@ def integrate_binary_evolution_2pwl(norm_log10, mtot, mrat, sepa_init, rchar, ga
         _lib.cy_consts(), _lib.ptr(nl), _lib.ptr(mt), _lib.ptr(mr), mt.numel(), float(sepa_init), float(rchar),
         float(gamma_inner), float(gamma_outer), int(nsteps), _lib.ptr(out), _lib.stream())
     _lib.check(rc, "integrate_binary_evolution_2pwl")
-    res = out.cpu().numpy()
+    res = _lib.to_host(out)
     return float(res[0]) if np.ndim(norm_log10) == 0 else res
 
 

@@ -30,7 +30,8 @@ def _rank_order(h2fdf, shape):
     return mq // Qb, mq % Qb, zsort
 
 
-def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=None, r0=0, _precomputed=None):
+def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=None, r0=0, device=False,
+                _precomputed=None):
     """Strain of the `loudest` loudest single sources and of the background, per frequency and realization.
 
     Parameters mirror ``single_sources.ss_gws_redz`` (``single_sources.py:40-85``):
@@ -39,10 +40,11 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
     ``realize`` integer number of realizations.
 
     Returns ``hc_ss`` (F,R,L), ``hc_bg`` (F,R) and, if ``params``, ``sspar`` (4,F,R,L), ``bgpar`` (7,F,R)
-    (numpy arrays).
+    (numpy arrays; CUDA tensors with the keyword-only addition ``device=True``).
     """
     import torch
     _lib.require_gpu()
+    host = (lambda tt: tt) if device else _lib.to_host
     edges_np = [np.asarray(ee.cpu()) if _lib.is_device_array(ee) else np.asarray(ee, dtype=float) for ee in edges]
     # All other bin midpoints
     mt = utils.midpoints(edges_np[0])   #: total mass
@@ -76,21 +78,22 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
             number_d, h2fdf, realize, loudest,
             mt, mr, rz, strain["zmid"], strain["dcom"], strain["sepa"], strain["angs"],
             msort, qsort, zsort, seed=seed, r0=r0, device=True)
-        hc_ss = torch.sqrt(hc2ss).cpu().numpy()
-        hc_bg = torch.sqrt(hc2bg).cpu().numpy()
-        sspar = sspar.cpu().numpy()
-        bgpar = bgpar.cpu().numpy()
+        hc_ss = host(torch.sqrt(hc2ss))
+        hc_bg = host(torch.sqrt(hc2bg))
+        sspar = host(sspar)
+        bgpar = host(bgpar)
         # check that all final redshifts are positive or -1
-        if np.any(np.logical_and(sspar[3] < 0, sspar[3] != -1)):
-            err = np.sum(np.logical_and(sspar[3] < 0, sspar[3] != -1))
+        bad = (sspar[3] < 0) & (sspar[3] != -1)
+        if bool(bad.any()):
+            err = int(bad.sum())
             err = f"check 1: {err} out of {sspar[3].size} sspar[3] are negative and not -1 in sings.ss_gws_redz()"
             raise ValueError(err)
         return hc_ss, hc_bg, sspar, bgpar
 
     hc2ss, hc2bg = cyutils.loudest_hc_from_sorted(number_d, h2fdf, realize, loudest, msort, qsort, zsort,
                                                   seed=seed, r0=r0, device=True)
-    hc_ss = torch.sqrt(hc2ss).cpu().numpy()
-    hc_bg = torch.sqrt(hc2bg).cpu().numpy()
+    hc_ss = host(torch.sqrt(hc2ss))
+    hc_bg = host(torch.sqrt(hc2bg))
     return hc_ss, hc_bg
 
 
@@ -115,11 +118,11 @@ def ss_gws(edges, number, realize, loudest=1, params=False, *, seed=None, r0=0):
     if params:
         hc2ss, hc2bg, lspar, bgpar, ssidx = cyutils.loudest_hc_and_par_from_sorted(
             number_d, h2fdf, realize, loudest, mt, mr, rz, msort, qsort, zsort, seed=seed, r0=r0, device=True)
-        ssidx = ssidx.cpu().numpy()
-        hc_ss = torch.sqrt(hc2ss).cpu().numpy()
-        hc_bg = torch.sqrt(hc2bg).cpu().numpy()
+        ssidx = _lib.to_host(ssidx)
+        hc_ss = _lib.to_host(torch.sqrt(hc2ss))
+        hc_bg = _lib.to_host(torch.sqrt(hc2bg))
         sspar = np.array([mt[ssidx[0]], mr[ssidx[1]], rz[ssidx[2]]])
-        return hc_ss, hc_bg, sspar, bgpar.cpu().numpy()
+        return hc_ss, hc_bg, sspar, _lib.to_host(bgpar)
     hc2ss, hc2bg = cyutils.loudest_hc_from_sorted(number_d, h2fdf, realize, loudest, msort, qsort, zsort,
                                                   seed=seed, r0=r0, device=True)
-    return torch.sqrt(hc2ss).cpu().numpy(), torch.sqrt(hc2bg).cpu().numpy()
+    return _lib.to_host(torch.sqrt(hc2ss)), _lib.to_host(torch.sqrt(hc2bg))

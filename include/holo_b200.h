@@ -42,6 +42,13 @@ const char* holo_last_error(void);
 int holo_device_count(void);
 /* Running count of kernels this library has launched in this process (bench.py `gpu_launches`). */
 int64_t holo_launch_count(void);
+/* Optional per-kernel timing of the multi-kernel entry points (holo_loudest, holo_sam_poisson_gwb):
+ * when enabled they record CUDA events around their internal kernels on the caller's stream and
+ * synchronise before returning.  holo_get_profile copies the last call's stage durations [ms] --
+ * holo_loudest: {head preparation, draw kernel, resolve, final reduce}; holo_sam_poisson_gwb:
+ * {draw kernel, final reduce} -- and returns how many entries are valid.  Used by bench.py only. */
+void holo_set_profiling(int on);
+int holo_get_profile(double* ms, int n);
 
 /* Constants the reference computes once at import with libm (sam_cyutils.pyx:36-42).  The host
  * computes them the same way (libm pow/sqrt) and passes them in, so device code sees identical bits. */

@@ -75,12 +75,25 @@ def ref():
 # ==================================================================================================
 
 class OracleCosmo:
-    def __init__(self, h=0.6933, Om0=0.2880):
+    """``closed_form=False`` (default): every quantity by adaptive quadrature / Newton inversion --
+    slow, fully independent of the product's formulas; used for the golden fixtures.
+    ``closed_form=True``: the textbook flat-LCDM closed forms for ``age`` / ``tage_to_z`` and a dense
+    spline for ``comoving_distance`` -- what the CPU-baseline chain uses at the 91x81x101 grid
+    (checked against the quadrature versions in tests/test_oracle.py)."""
+
+    def __init__(self, h=0.6933, Om0=0.2880, closed_form=False):
         self.h = h
         self.Om0 = Om0
         self.H0_cgs = 100.0 * h * 1.0e5 / MPC
         self.hubble_time = 1.0 / self.H0_cgs
         self.hubble_distance = SPLC / self.H0_cgs
+        if closed_form:
+            ol = 1.0 - Om0
+            self.age = lambda zz: (2.0 / 3.0) * self.hubble_time / np.sqrt(ol) * np.arcsinh(
+                np.sqrt(ol / Om0) * np.power(1.0 + np.asarray(zz, dtype=float), -1.5))
+            self.tage_to_z = lambda tt: np.power(
+                np.sqrt(ol / Om0) / np.sinh(1.5 * np.sqrt(ol) * np.asarray(tt, dtype=float) / self.hubble_time), 2.0 / 3.0) - 1.0
+            self.comoving_distance = self.comoving_distance_fast
 
     def efunc(self, zz):
         return np.sqrt(self.Om0 * (1.0 + zz)**3 + (1.0 - self.Om0))
