@@ -12,9 +12,11 @@
 #if defined(__CUDACC__)
 #define HOLO_HD __host__ __device__ __forceinline__
 #define HOLO_D __device__ __forceinline__
+#define HOLO_NOINLINE __host__ __device__ __noinline__
 #else
 #define HOLO_HD inline
 #define HOLO_D inline
+#define HOLO_NOINLINE inline
 #endif
 
 namespace holo {

@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 
 #include "holo_api.cuh"
+#include <string.h>
+
 #include "holo_rng.cuh"
 
 namespace holo {
@@ -81,29 +83,86 @@ struct RealizeArgs {
     double thresh;
 };
 
+// One staged CELL: the (up to) FGROUP frequencies of the CTA's frequency group that are non-empty.
+// Everything a draw needs sits here so the per-realization loop touches shared memory only.
 template <int NACC>
-struct Entry {
-    DrawPrep prep;
-    double h;
-    double w[NACC > 1 ? NACC - 1 : 1];
+struct CellEntry {
+    FPrep f[FGROUP];                                    // sampler set-up + h2fdf per frequency
+    double w3[NACC > 1 ? 3 : 1];                        // mt, mr, rz of the cell (parameter variants)
+    double w4[NACC > 4 ? FGROUP : 1][NACC > 4 ? 4 : 1];  // redz_final, dcom, sepa, angs per frequency
     int cell;
-    int head;   // 1: occupied draws go to the event bucket (rank < K_f); also carries the rank
+    unsigned char cls[FGROUP];                          // CLS_* per frequency
+    unsigned char head[FGROUP];                         // 1: occupied draws go to the event bucket
 };
 
 template <int VARIANT>
-__global__ void __launch_bounds__(RZ_THREADS)
+__host__ __device__ constexpr int sub_of() {
+    // cells staged per pass, sized so that the staging buffer stays below 48 KB of static smem
+    return nacc_of(VARIANT) > 4 ? 128 : 192;
+}
+
+// Fold one draw `n` of staged cell `e`, frequency slot `fi`, into the thread's accumulators (or the
+// event bucket).  Shared by the lock-step phase and the lane-decoupled PTRS phase.
+template <int VARIANT, class Ent>
+__device__ __forceinline__ void fold_draw(const RealizeArgs& a, const Ent& e, int fi, int f, int r, double n,
+                                          double (&acc)[nacc_of(VARIANT)], double& vmax, int& imax) {
+    constexpr int NACC = nacc_of(VARIANT);
+    const double cur = e.f[fi].h;
+    if (VARIANT == V_GWB) {
+        acc[0] += n * cur;                                                  // pyx:891, 895
+    } else if (has_max(VARIANT)) {
+        // `if (cur > max and num > 0)` walking cells in natural order (pyx:993, 1134): the first cell
+        // holding the maximum wins.  Cells are not visited in natural order here, hence the index tie-break.
+        if (n > 0.0 && (cur > vmax || (cur == vmax && cur > 0.0 && e.cell < imax))) { vmax = cur; imax = e.cell; }
+        const double nc = n * cur;
+        acc[0] += nc;                                                       // pyx:998, 1139
+        if (NACC > 1) {
+#pragma unroll
+            for (int k = 1; k < 4; ++k) acc[k < NACC ? k : 0] += nc * e.w3[k - 1];
+        }
+    } else {
+        if (n < 1.0) return;                                                // pyx:1333, 1490, 1727
+        if (e.head[fi]) {
+            const int slot = atomicAdd(&a.evcount[(int64_t)f * a.R + r], 1);
+            if (slot < a.cap) {
+                Event ev;
+                ev.rank = a.rank[e.cell];
+                ev.cell = e.cell;
+                ev.n = n;
+                a.events[((int64_t)f * a.R + r) * a.cap + slot] = ev;
+            }
+        } else {
+            const double nc = n * cur;
+            acc[0] += nc;                                                   // pyx:1342, 1505, 1745
+            if (NACC > 1) {
+#pragma unroll
+                for (int k = 1; k < 4; ++k) acc[k < NACC ? k : 0] += nc * e.w3[k - 1];
+            }
+            if (NACC > 4) {
+#pragma unroll
+                for (int k = 4; k < 8; ++k) acc[k < NACC ? k : 0] += nc * e.w4[fi][k - 4];
+            }
+        }
+    }
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(RZ_THREADS, nacc_of(VARIANT) == 1 ? 3 : 2)
 realize_kernel(RealizeArgs a) {
     constexpr int NACC = nacc_of(VARIANT);
-    using Ent = Entry<NACC>;
-    constexpr int SUBV = NACC > 4 ? SUB / 2 : SUB;   // keep the staging buffer under 48 KB static smem
+    using Ent = CellEntry<NACC>;
+    constexpr int SUBV = sub_of<VARIANT>();
     __shared__ Ent s_ent[SUBV];
-    __shared__ int s_wcount[RZ_THREADS / 32];
-    __shared__ int s_total;
+    __shared__ unsigned short s_plist[FGROUP][SUBV];   // per frequency slot: staged cells of class PTRS
+    __shared__ int s_np[FGROUP];
+    __shared__ int s_wcount[FGROUP + 1][RZ_THREADS / 32];
+    __shared__ double s_rcp[RCP_TABLE];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarp = blockDim.x >> 5;
     const int chunk_id = blockIdx.x;
-    const int f0 = blockIdx.y * FGROUP;
+    const int fg = blockIdx.y;
+    const int f0 = fg * FGROUP;
     const int r = blockIdx.z * blockDim.x + tid;      // local realization
     const bool live = r < a.R;
     const int64_t c_lo = (int64_t)chunk_id * a.chunk;
@@ -111,6 +170,8 @@ realize_kernel(RealizeArgs a) {
     if (c_hi > a.ncell) c_hi = a.ncell;
     const int nf = (a.F - f0) < FGROUP ? (a.F - f0) : FGROUP;
     const bool supplied = a.counts != nullptr;
+
+    if (tid < RCP_TABLE) s_rcp[tid] = tid > 0 ? 1.0 / (double)tid : 0.0;
 
     double acc[FGROUP][NACC];
     double vmax[FGROUP];
@@ -129,107 +190,180 @@ realize_kernel(RealizeArgs a) {
     key.stream = has_events(VARIANT) ? STREAM_LOUD : (has_max(VARIANT) ? STREAM_SSBG : STREAM_GWB);
 
     for (int64_t cb = c_lo; cb < c_hi; cb += SUBV) {
+        // ---- stage the non-empty cells of [cb, cb+SUBV) in cell order (deterministic compaction), and
+        //      list, per frequency slot, the staged cells whose draw is a PTRS rejection sampler
+        __syncthreads();   // previous pass fully consumed
+        int base = 0;
+        int pbase[FGROUP] = {0, 0, 0, 0};
+        for (int off = 0; off < SUBV; off += blockDim.x) {
+            const int64_t c = cb + off + tid;
+            const bool inrange = (c < c_hi) && (off + tid < SUBV);
+            // pass 1: classify only (cheap) so that the compaction offsets are known before any set-up work
+            unsigned clsw = 0;   // CLS_* byte per frequency slot
+            if (inrange) {
 #pragma unroll
-        for (int fi = 0; fi < FGROUP; ++fi) {
-            if (fi >= nf) break;
-            const int f = f0 + fi;
-            // ---- stage the non-empty elements of cells [cb, cb+SUB) at frequency f, in cell order
-            __syncthreads();   // previous pass fully consumed
-            int base = 0;
-            for (int off = 0; off < SUBV; off += blockDim.x) {
-                int64_t c = cb + off + tid;
-                double lam = 0.0, h = 0.0;
-                bool keep = false;
-                if (c < c_hi && off + tid < SUBV) {
-                    lam = a.number[c * a.F + f];
-                    h = a.h2fdf[c * a.F + f];
-                    keep = supplied || (lam > 0.0);
-                    if (VARIANT == V_LOUD_PAR_REDZ) keep = keep && (h != 0.0);   // pyx:1727
-                }
-                unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (lane == 0) s_wcount[warp] = __popc(bal);
-                __syncthreads();
-                int pos = base;
-                for (int w = 0; w < warp; ++w) pos += s_wcount[w];
-                pos += __popc(bal & ((1u << lane) - 1u));
-                if (keep) {
-                    Ent e;
-                    e.prep = prep_draw(lam, a.thresh);
-                    e.h = h;
-                    e.cell = (int)c;
-                    e.head = 0;
-                    if (has_events(VARIANT)) {
-                        int rk = a.rank[c];
-                        e.head = (rk < a.kf[f]) ? 1 : 0;
+                for (int fi = 0; fi < FGROUP; ++fi) {
+                    if (fi < nf) {
+                        const double lam = a.number[c * a.F + f0 + fi];
+                        int cls = classify_draw(lam, a.thresh);
+                        if (supplied) cls = CLS_SMALL;                               // every cell is read from `counts`
+                        if (VARIANT == V_LOUD_PAR_REDZ && a.h2fdf[c * a.F + f0 + fi] == 0.0) cls = CLS_EMPTY;   // pyx:1727
+                        clsw |= (unsigned)cls << (8 * fi);
                     }
-                    if (NACC > 1) {
-                        int zz = (int)(c % a.Zb);
-                        int64_t mq = c / a.Zb;
-                        int qq = (int)(mq % a.Qb);
-                        int mm = (int)(mq / a.Qb);
-                        e.w[0] = a.mt[mm];
-                        if (NACC > 2) { e.w[1] = a.mr[qq]; e.w[2] = a.rz[zz]; }
+                }
+            }
+            const bool keep = clsw != 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            unsigned pbal[FGROUP];
+#pragma unroll
+            for (int fi = 0; fi < FGROUP; ++fi)
+                pbal[fi] = __ballot_sync(0xffffffffu, ((clsw >> (8 * fi)) & 0xff) == CLS_PTRS);
+            if (lane == 0) {
+                s_wcount[FGROUP][warp] = __popc(bal);
+#pragma unroll
+                for (int fi = 0; fi < FGROUP; ++fi) s_wcount[fi][warp] = __popc(pbal[fi]);
+            }
+            __syncthreads();
+            int pos = base;
+            for (int w = 0; w < warp; ++w) pos += s_wcount[FGROUP][w];
+            pos += __popc(bal & ((1u << lane) - 1u));
+            int tot = 0;
+            for (int w = 0; w < nwarp; ++w) tot += s_wcount[FGROUP][w];
+#pragma unroll
+            for (int fi = 0; fi < FGROUP; ++fi) {
+                int pp = pbase[fi], pt = 0;
+                for (int w = 0; w < nwarp; ++w) {
+                    if (w < warp) pp += s_wcount[fi][w];
+                    pt += s_wcount[fi][w];
+                }
+                if (((clsw >> (8 * fi)) & 0xff) == CLS_PTRS)
+                    s_plist[fi][pp + __popc(pbal[fi] & ((1u << lane) - 1u))] = (unsigned short)pos;
+                pbase[fi] += pt;
+            }
+            // pass 2: the owner of a kept cell fills its slot in place (no big struct in registers)
+            if (keep) {
+                Ent& e = s_ent[pos];
+                e.cell = (int)c;
+                int rk = 0;
+                if (has_events(VARIANT)) rk = a.rank[c];
+#pragma unroll
+                for (int fi = 0; fi < FGROUP; ++fi) {
+                    const int cls = (clsw >> (8 * fi)) & 0xff;
+                    e.cls[fi] = (unsigned char)cls;
+                    e.head[fi] = 0;
+                    if (cls != CLS_EMPTY) {
+                        const int64_t o = c * a.F + f0 + fi;
+                        prep_draw(a.number[o], a.thresh, e.f[fi]);
+                        e.f[fi].h = a.h2fdf[o];
+                        if (has_events(VARIANT)) e.head[fi] = (rk < a.kf[f0 + fi]) ? 1 : 0;
                         if (NACC > 4) {
-                            e.w[3] = a.redz_final[c * a.F + f];
-                            e.w[4] = a.dcom_final[c * a.F + f];
-                            e.w[5] = a.sepa[c * a.F + f];
-                            e.w[6] = a.angs[c * a.F + f];
+                            e.w4[fi][0] = a.redz_final[o];
+                            e.w4[fi][1] = a.dcom_final[o];
+                            e.w4[fi][2] = a.sepa[o];
+                            e.w4[fi][3] = a.angs[o];
                         }
                     }
-                    s_ent[pos] = e;
                 }
-                if (tid == 0) {
-                    int tot = 0;
-                    for (int w = 0; w < nwarp; ++w) tot += s_wcount[w];
-                    s_total = base + tot;
+                if (NACC > 1) {
+                    const int zz = (int)(c % a.Zb);
+                    const int64_t mq = c / a.Zb;
+                    e.w3[0] = a.mt[(int)(mq / a.Qb)];
+                    e.w3[1] = a.mr[(int)(mq % a.Qb)];
+                    e.w3[2] = a.rz[zz];
                 }
-                __syncthreads();
-                base = s_total;
             }
-            const int count = base;
-            if (!live) continue;
+            base += tot;
+            __syncthreads();   // s_wcount is rewritten by the next round
+        }
+        const int count = base;
+        if (tid == 0) {
+#pragma unroll
+            for (int fi = 0; fi < FGROUP; ++fi) s_np[fi] = pbase[fi];
+        }
+        __syncthreads();
+        if (!live) continue;
 
-            // ---- every thread (= realization) walks the staged list
+        if (supplied) {
+            // ---- supplied-count mode: no random numbers at all
             for (int i = 0; i < count; ++i) {
                 const Ent& e = s_ent[i];
-                double n;
-                if (supplied) {
-                    n = a.counts[((int64_t)r * a.F + f) * a.ncell + e.cell];
-                } else {
-                    uint64_t idx = (uint64_t)e.cell * (uint64_t)a.F + (uint64_t)f;
-                    key.idx_lo = (uint32_t)idx;
-                    key.idx_hi = (uint32_t)(idx >> 32);
-                    n = draw_count(e.prep, key);
+#pragma unroll
+                for (int fi = 0; fi < FGROUP; ++fi) {
+                    if (e.cls[fi] == CLS_EMPTY) continue;
+                    const int f = f0 + fi;
+                    const double n = a.counts[((int64_t)r * a.F + f) * a.ncell + e.cell];
+                    fold_draw<VARIANT>(a, e, fi, f, r, n, acc[fi], vmax[fi], imax[fi]);
                 }
-                if (VARIANT == V_GWB) {
-                    acc[fi][0] += n * e.h;                                   // pyx:891, 895
-                } else if (has_max(VARIANT)) {
-                    double cur = e.h;
-                    if (cur > vmax[fi] && n > 0.0) { vmax[fi] = cur; imax[fi] = e.cell; }   // pyx:993, 1134
-                    double nc = n * cur;
-                    acc[fi][0] += nc;                                        // pyx:998, 1139
-                    if (NACC > 1) {
+            }
+            continue;
+        }
+
+        // ---- phase A, lock-step: every thread (= realization) walks the staged cells; TINY / SMALL /
+        //      NORMAL draws of the four frequencies share one (two) Philox blocks per cell
+        for (int i = 0; i < count; ++i) {
+            const Ent& e = s_ent[i];
+            const uint32_t cell = (uint32_t)e.cell;
+            uint32_t clsw;   // the four class bytes, warp-uniform
+            memcpy(&clsw, e.cls, 4);
+            // bytes equal to CLS_TINY (1) / CLS_SMALL (2)?  (classic has-zero-byte test on clsw ^ pattern)
+            const uint32_t t1 = clsw ^ 0x01010101u, t2 = clsw ^ 0x02020202u;
+            const bool any_tiny = ((t1 - 0x01010101u) & ~t1 & 0x80808080u) != 0;
+            const bool any_small = ((t2 - 0x01010101u) & ~t2 & 0x80808080u) != 0;
+            Philox4 hi, lo;
+            if (any_tiny || any_small) hi = group_bits(key, cell, (uint32_t)fg, PURPOSE_GROUP_HI);
+            if (any_small) lo = group_bits(key, cell, (uint32_t)fg, PURPOSE_GROUP_LO);
 #pragma unroll
-                        for (int k = 1; k < NACC; ++k) acc[fi][k] += nc * e.w[k - 1];
-                    }
+            for (int fi = 0; fi < FGROUP; ++fi) {
+                const int cls = (clsw >> (8 * fi)) & 0xff;
+                if (cls == CLS_EMPTY || cls == CLS_PTRS) continue;
+                const int f = f0 + fi;
+                const FPrep& p = e.f[fi];
+                const uint64_t idx = (uint64_t)cell * (uint64_t)a.F + (uint64_t)f;
+                double n;
+                if (cls == CLS_TINY) n = draw_tiny(p, hi.v[fi], key, idx);
+                else if (cls == CLS_SMALL) n = draw_small(p, hi.v[fi], lo.v[fi], s_rcp);
+                else n = draw_normal(p, key, idx);
+                fold_draw<VARIANT>(a, e, fi, f, r, n, acc[fi], vmax[fi], imax[fi]);
+            }
+        }
+
+        // ---- phase B, lane-decoupled: each lane walks the PTRS list of a frequency slot at its own pace
+        //      (one rejection trial per loop turn), so a rejected proposal delays only its own lane
+#pragma unroll 1
+        for (int fi = 0; fi < FGROUP; ++fi) {
+            const int np = s_np[fi];
+            if (np == 0) continue;
+            const int f = f0 + fi;
+            // slot-local accumulators keep `acc` in registers (fi is a run-time index in this loop)
+            double lacc[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) lacc[k] = 0.0;
+            double lvmax = 0.0;
+            int limax = -1;
+            int it = 0;
+            uint32_t trial = 0;
+            while (it < np) {
+                const Ent& e = s_ent[s_plist[fi][it]];
+                const uint64_t idx = (uint64_t)(uint32_t)e.cell * (uint64_t)a.F + (uint64_t)f;
+                double k;
+                const bool ok = ptrs_trial(e.f[fi], element_bits(key, idx, trial), &k);
+                if (ok) {
+                    fold_draw<VARIANT>(a, e, fi, f, r, k, lacc, lvmax, limax);
+                    ++it;
+                    trial = 0;
                 } else {
-                    if (n < 1.0) continue;                                   // pyx:1333, 1490, 1727
-                    if (e.head) {
-                        int slot = atomicAdd(&a.evcount[(int64_t)f * a.R + r], 1);
-                        if (slot < a.cap) {
-                            Event ev;
-                            ev.rank = a.rank[e.cell];
-                            ev.cell = e.cell;
-                            ev.n = n;
-                            a.events[((int64_t)f * a.R + r) * a.cap + slot] = ev;
-                        }
-                    } else {
-                        double nc = n * e.h;
-                        acc[fi][0] += nc;                                    // pyx:1342, 1505, 1745
-                        if (NACC > 1) {
+                    ++trial;
+                }
+            }
 #pragma unroll
-                            for (int k = 1; k < NACC; ++k) acc[fi][k] += nc * e.w[k - 1];
-                        }
+            for (int j = 0; j < FGROUP; ++j) {
+                if (j == fi) {
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) acc[j][k] += lacc[k];
+                    if (has_max(VARIANT) && limax >= 0 &&
+                        (lvmax > vmax[j] || (lvmax == vmax[j] && limax < imax[j]))) {
+                        vmax[j] = lvmax;
+                        imax[j] = limax;
                     }
                 }
             }
@@ -551,16 +685,11 @@ bulk_poisson_kernel(const double* __restrict__ lam, int64_t n, uint32_t k0, uint
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         double l = lam[i];
-        double v = 0.0;
-        if (l > 0.0) {
-            DrawPrep p = prep_draw(l, thresh);
-            DrawKey key;
-            key.k0 = k0; key.k1 = k1;
-            key.idx_lo = (uint32_t)i; key.idx_hi = (uint32_t)((uint64_t)i >> 32);
-            key.real = stream_id; key.stream = STREAM_BULK;
-            v = draw_count(p, key);
-            if (p.cls == CLS_NORMAL) v = floor(v);
-        }
+        DrawKey key;
+        key.k0 = k0; key.k1 = k1;
+        key.real = stream_id; key.stream = STREAM_BULK;
+        double v = draw_element(l, thresh, key, (uint64_t)i);
+        if (l > thresh) v = floor(v);
         out[i] = v;
     }
 }

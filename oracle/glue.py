@@ -230,13 +230,27 @@ def gw_lum_circ(mchirp, freq_orb_rest):
     return _GW_LUM_CONST * np.power(2.0*np.pi*freq_orb_rest*mchirp, 10.0/3.0)
 
 
-def gw_hardening_rate_dfdt(m1, m2, frst_orb, eccen=None):
-    """utils.py:2186-2222"""
-    mchirp = chirp_mass(m1, m2)
-    dfdt = (96.0/5.0) * np.power(NWTG*mchirp/SPLC**3, 5.0/3.0) * np.power(2.0*np.pi*frst_orb, 11.0/3.0) / (2.0*np.pi)
-    if eccen is not None:
-        dfdt = dfdt * _gw_ecc_func(eccen)
+def dfdt_from_dadt(dadt, sepa, mtot=None, frst_orb=None):
+    """utils.py:1554-1587"""
+    if frst_orb is None:
+        frst_orb = kepler_freq_from_sepa(mtot, sepa)
+    dfdt = -1.5 * (frst_orb / sepa) * dadt
     return dfdt, frst_orb
+
+
+def gw_hardening_rate_dfdt(m1, m2, frst_orb, eccen=None):
+    """utils.py:2186-2211"""
+    m1, m2, frst_orb = [np.asarray(vv) for vv in (m1, m2, frst_orb)]
+    sepa = kepler_sepa_from_freq(m1+m2, frst_orb)
+    dfdt = gw_hardening_rate_dadt(m1, m2, sepa, eccen=None if eccen is None else np.asarray(eccen))
+    dfdt, _ = dfdt_from_dadt(dfdt, sepa, frst_orb=frst_orb)
+    return dfdt, frst_orb
+
+
+def gw_hardening_timescale_freq(mchirp, frst):
+    """utils.py:2214-2234"""
+    mchirp, frst = np.asarray(mchirp), np.asarray(frst)
+    return (5.0 / 96.0) * np.power(NWTG*mchirp/SPLC**3, -5.0/3.0) * np.power(2*np.pi*frst, -8.0/3.0)
 
 
 def kepler_freq_from_sepa(mass, sepa):

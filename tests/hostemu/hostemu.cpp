@@ -194,3 +194,49 @@ void emu_integrate_and_strain(const holo_cosmo_params* cosmo, double gw_src_cons
 }
 
 }  // extern "C"
+
+// ---- samplers (holo_rng.cuh) ---------------------------------------------------------------------
+#include "../../holodeck_b200/csrc/holo_rng.cuh"
+
+extern "C" {
+
+// n independent draws of Poisson(lam) (realization index = 0..n-1) through the stand-alone path
+void emu_draw_elements(double lam, int64_t n, uint64_t seed, double thresh, uint64_t idx, double* out) {
+    DrawKey key;
+    key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32); key.stream = 7;
+    for (int64_t i = 0; i < n; ++i) {
+        key.real = (uint32_t)i;
+        out[i] = draw_element(lam, thresh, key, idx);
+    }
+}
+
+// n draws through the shared-group path used by the realization kernel: 4 frequencies of one cell
+// share a HI block (and a LO block for the SMALL class); lam4 holds the 4 expectation values.
+void emu_draw_group(const double* lam4, int64_t n, uint64_t seed, double thresh, uint32_t cell, double* out /* (n,4) */) {
+    DrawKey key;
+    key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32); key.stream = 2;
+    FPrep p[4];
+    int cls[4];
+    for (int j = 0; j < 4; ++j) cls[j] = prep_draw(lam4[j], thresh, p[j]);
+    for (int64_t i = 0; i < n; ++i) {
+        key.real = (uint32_t)i;
+        Philox4 hi = group_bits(key, cell, 3, PURPOSE_GROUP_HI);
+        Philox4 lo = group_bits(key, cell, 3, PURPOSE_GROUP_LO);
+        for (int j = 0; j < 4; ++j) {
+            uint64_t idx = (uint64_t)cell * 40 + 12 + j;
+            double v = 0.0;
+            if (cls[j] == CLS_TINY) v = draw_tiny(p[j], hi.v[j], key, idx);
+            else if (cls[j] == CLS_SMALL) v = draw_small(p[j], hi.v[j], lo.v[j]);
+            else if (cls[j] == CLS_PTRS) v = draw_ptrs(p[j], key, idx);
+            else if (cls[j] == CLS_NORMAL) v = draw_normal(p[j], key, idx);
+            out[i * 4 + j] = v;
+        }
+    }
+}
+
+void emu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+    Philox4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    for (int i = 0; i < 4; ++i) out[i] = r.v[i];
+}
+
+}  // extern "C"
