@@ -43,3 +43,5 @@ from holodeck_b200 import gravwaves       # noqa: E402,F401
 from holodeck_b200 import single_sources  # noqa: E402,F401
 from holodeck_b200 import sams            # noqa: E402,F401
 from holodeck_b200.sams import sam        # noqa: E402,F401
+from holodeck_b200 import dist            # noqa: E402,F401
+from holodeck_b200 import librarian       # noqa: E402,F401

@@ -112,6 +112,13 @@ def cy_consts():
     return cc
 
 
+def cy_gw_src_const():
+    """``GW_SRC_CONST`` of ``cyutils.pyx:48`` evaluated with libm in the same order."""
+    nwtg = 6.6742999e-08
+    splc = 29979245800.0
+    return 8.0 * math.pow(nwtg, 5.0/3.0) * math.pow(math.pi, 2.0/3.0) / math.sqrt(10.0) / math.pow(splc, 4.0)
+
+
 def cosmo_params(cosmo):
     from .cosmology import _GL_X, _GL_W
     cp = CosmoParams()
@@ -160,7 +167,7 @@ SIGNATURES = {
                       _P, _L, _P],
     "holo_realize_workspace_bytes": [_I, _L, _I, _I],
     "holo_poisson_as_needed": [_P, _L, _U, _U, _D, _P, _P],
-    "holo_sam_calc_gwb_single_eccen": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I,
+    "holo_sam_calc_gwb_single_eccen": [CyConsts, _D, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I,
                                        _L, _U, _P, _P, _L, _P],
     "holo_eccen_workspace_bytes": [_I, _I, _I, _I, _I, _I],
 }

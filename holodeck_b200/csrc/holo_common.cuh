@@ -12,11 +12,11 @@
 #if defined(__CUDACC__)
 #define HOLO_HD __host__ __device__ __forceinline__
 #define HOLO_D __device__ __forceinline__
-#define HOLO_NOINLINE __host__ __device__ __noinline__
+#define HOLO_NOINLINE_STATIC static __host__ __device__ __noinline__
 #else
 #define HOLO_HD inline
 #define HOLO_D inline
-#define HOLO_NOINLINE inline
+#define HOLO_NOINLINE_STATIC static inline
 #endif
 
 namespace holo {

@@ -201,7 +201,7 @@ HOLO_HD double log_factorial_small(int k) {
 }
 
 // Exact PTRS acceptance test:  log(V*invalpha/(a/us^2+b)) <= -lam + k log(lam) - log(k!)
-HOLO_NOINLINE bool ptrs_accept(double lam, double inv_lam, double a, double b, double us, double V, double k) {
+HOLO_NOINLINE_STATIC bool ptrs_accept(double lam, double inv_lam, double a, double b, double us, double V, double k) {
     double invalpha = 1.1239 + 1.1328 / (b - 3.4);
     double den = a / (us * us) + b;
     if (k >= 10.0) {

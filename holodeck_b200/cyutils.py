@@ -274,6 +274,7 @@ def _eccen(ndens, mtot_log10, mrat, redz, dcom, gwfobs, sepa_evo, eccen_evo, nha
     gwb = _lib.empty((F, H) if R == 0 else (F, H, R))
     ws = _workspace(lib.holo_eccen_workspace_bytes(M, Q, Z, F, H, R))
     rc = lib.holo_sam_calc_gwb_single_eccen(
+        _lib.cy_consts(), _lib.cy_gw_src_const(),
         _lib.ptr(ndens), *[_lib.ptr(aa) for aa in arrs], M, Q, Z, F, E, H, R, int(r0), _seed(seed),
         _lib.ptr(gwb), _lib.ptr(ws), ws.numel(), _lib.stream())
     _lib.check(rc, "sam_calc_gwb_single_eccen")

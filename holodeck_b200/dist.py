@@ -1,0 +1,95 @@
+"""Multi-GPU sharding of the SAM hot path: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The path shards by *independent units* (SURVEY.md section 8e), with no collective on the data path:
+
+* **realizations** -- every rank holds a replica of the deterministic grids (they are recomputed
+  locally: cheaper than broadcasting 1 GB) and draws its slice of the R realizations; the Philox
+  counter is keyed on the GLOBAL realization index, so the union over ranks is bit-identical to a
+  single-GPU run.  One ``all_gather`` of the small per-rank ``hc`` tables at the end (NCCL).
+* **library samples** -- the parameter samples of a library are permuted and split over ranks exactly
+  as ``holodeck/librarian/gen_lib.py:139-141,169`` does over MPI ranks.
+
+On CPU-only machines the same code runs on the ``gloo`` backend (tests use world_size 2).
+"""
+import os
+
+import numpy as np
+
+
+def is_distributed():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized()
+
+
+def world():
+    """(rank, world_size) of this process (``(0, 1)`` when not launched under torchrun)."""
+    if is_distributed():
+        import torch.distributed as dist
+        return dist.get_rank(), dist.get_world_size()
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def init(backend=None):
+    """Initialise the default process group from the torchrun environment (no-op for world size 1)."""
+    import torch
+    import torch.distributed as dist
+    size = int(os.environ.get("WORLD_SIZE", "1"))
+    if size <= 1 or dist.is_initialized():
+        return world()
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend)
+    return world()
+
+
+def realization_slice(nreals, rank=None, size=None):
+    """Contiguous slice ``(r0, count)`` of ``nreals`` realizations owned by ``rank`` (sizes differ by <= 1)."""
+    if rank is None or size is None:
+        rank, size = world()
+    base, extra = divmod(int(nreals), size)
+    count = base + (1 if rank < extra else 0)
+    r0 = rank * base + min(rank, extra)
+    return r0, count
+
+
+def gather_realizations(tensor, axis=1, nreals=None):
+    """All-gather per-rank result tables along the realization ``axis`` (ragged slices allowed)."""
+    import torch
+    import torch.distributed as dist
+    if not is_distributed() or dist.get_world_size() == 1:
+        return tensor
+    size = dist.get_world_size()
+    if nreals is None:
+        counts = [tensor.shape[axis]] * size
+    else:
+        counts = [realization_slice(nreals, rr, size)[1] for rr in range(size)]
+    cmax = max(counts)
+    moved = tensor.movedim(axis, 0).contiguous()
+    if moved.shape[0] < cmax:   # pad ragged slices so every rank sends the same shape
+        pad = torch.zeros((cmax - moved.shape[0],) + tuple(moved.shape[1:]), dtype=moved.dtype, device=moved.device)
+        moved = torch.cat([moved, pad], dim=0)
+    outs = [torch.empty_like(moved) for _ in range(size)]
+    dist.all_gather(outs, moved)
+    full = torch.cat([oo[:cc] for oo, cc in zip(outs, counts)], dim=0)
+    return full.movedim(0, axis).contiguous()
+
+
+def sample_indices(nsamples, seed=None, rank=None, size=None):
+    """Indices of the library samples this rank runs: permute, then ``array_split`` over ranks
+    (``gen_lib.py:139-141``).  Every rank computes the same permutation from ``seed``."""
+    if rank is None or size is None:
+        rank, size = world()
+    rng = np.random.RandomState(seed)
+    indices = rng.permutation(np.arange(nsamples))
+    return np.array_split(indices, size)[rank]
+
+
+def barrier():
+    if is_distributed():
+        import torch.distributed as dist
+        dist.barrier()

@@ -279,7 +279,9 @@ int holo_poisson_as_needed(const double* lam, int64_t n, uint64_t seed, uint64_t
  *     _sam_calc_gwb_single_eccen           holodeck/cyutils.pyx:370-597   -> gwb (F,H)
  *     _sam_calc_gwb_single_eccen_discrete  holodeck/cyutils.pyx:609-851   -> gwb (F,H,R)
  * --------------------------------------------------------------------------------------------- */
-int holo_sam_calc_gwb_single_eccen(const double* ndens /* (M,Q,Z) */, const double* mtot_log10,
+int holo_sam_calc_gwb_single_eccen(holo_cy_consts cc /* cyutils.pyx:47 GW_DADT_SEP_CONST */,
+                                   double gw_src_const /* cyutils.pyx:48, libm-evaluated by the host */,
+                                   const double* ndens /* (M,Q,Z) */, const double* mtot_log10,
                                    const double* mrat, const double* redz, const double* dcom_mpc,
                                    const double* gwfobs, const double* sepa_evo,
                                    const double* eccen_evo, int M, int Q, int Z, int F, int E,

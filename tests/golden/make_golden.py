@@ -139,7 +139,43 @@ def sam_case(name, shape, nfreq, pta_dur_yr, kind, seed, nreals, nloud, hard='2p
           f"occupied draws/realization ~ {np.minimum(number,1).sum():.0f}")
 
 
+
+
+def eccen_case(name="eccen_small"):
+    """Eccentric GWB (cyutils.sam_calc_gwb_single_eccen[_discrete]) on a small synthetic SAM."""
+    cy, _, _ = G.ref()
+    M, Q, Z, F, H, E = 9, 8, 10, 5, 20, 123
+    mtot = np.logspace(np.log10(1e7*G.MSOL), np.log10(1e11*G.MSOL), M)
+    mrat = np.logspace(-2, 0, Q)
+    redz = np.logspace(-2, 0.7, Z)
+    rng = np.random.default_rng(1)
+    ndens = rng.uniform(0, 1e-3, (M, Q, Z))
+    ndens[rng.uniform(size=ndens.shape) < 0.2] = 0.0
+    oc = G.OracleCosmo()
+    dcom = oc.comoving_distance(redz) / G.MPC
+    fobs, _ = G.pta_freqs(16.03*G.YR, F)
+    out = dict(ndens=ndens, mtot=mtot, mrat=mrat, redz=redz, dcom=dcom, fobs=fobs, nharms=H)
+    for tag, a0 in (("a", 0.05*G.PC), ("b", 10.0*G.PC)):
+        sepa, ecc = G.evolve_eccen_uniform_single(mtot, 0.95, a0, E)
+        out[f"sepa_{tag}"] = sepa
+        out[f"eccen_{tag}"] = ecc
+        out[f"gwb_{tag}"] = np.asarray(cy.sam_calc_gwb_single_eccen(ndens, np.log10(mtot), mrat, redz, dcom, fobs, sepa, ecc, H))
+    # discrete: a seeded reference run; only its moments / quantiles are compared (different RNG)
+    cy.ORACLE_SEED = 31415
+    R = 400
+    scale = 3e7   # boost the densities so that the Poisson numbers are O(1-100), not all zero
+    out["disc_scale"] = scale
+    out["disc_R"] = R
+    out["gwb_disc_a"] = np.asarray(cy.sam_calc_gwb_single_eccen_discrete(
+        ndens*scale, np.log10(mtot), mrat, redz, dcom, fobs, out["sepa_a"], out["eccen_a"], H, R))
+    cy.ORACLE_SEED = None
+    fname = OUT / f"{name}.npz"
+    np.savez_compressed(fname, **out)
+    print(f"{fname.name}: {fname.stat().st_size/1e6:.2f} MB")
+
+
 if __name__ == "__main__":
     sam_case("classic_2pwl", (13, 11, 15), 6, 16.03, 'classic', seed=12345, nreals=6, nloud=3)
     sam_case("default_gw", (10, 11, 12), 5, 10.0, 'default', seed=777, nreals=5, nloud=2, hard='gw')
     sam_case("double_2pwl", (9, 8, 10), 4, 16.03, 'double', seed=99, nreals=4, nloud=5)
+    eccen_case()

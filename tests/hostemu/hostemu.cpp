@@ -240,3 +240,58 @@ void emu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
 }
 
 }  // extern "C"
+
+// ---- eccentric GWB helpers (holo_eccen_math.cuh) -----------------------------------------------
+#include "../../holodeck_b200/csrc/holo_eccen_math.cuh"
+
+extern "C" {
+
+void emu_bessel_pair(int nn, double x, double* out2) { bessel_pair(nn, x, &out2[0], &out2[1]); }
+
+double emu_gw_freq_dist_func(int nn, double ee) { return gw_freq_dist_func(nn, ee); }
+
+// continuous eccentric GWB, same factorisation as the CUDA kernels (q-sum, then (f,n) sum over (z,M))
+void emu_eccen_gwb(double gw_dadt_sep_const, double gw_src_const, const double* ndens, const double* mtot_log10,
+                   const double* mrat, const double* redz, const double* dcom, const double* gwfobs,
+                   const double* sepa_evo, const double* eccen_evo, int M, int Q, int Z, int F, int E, int H,
+                   double* gwb) {
+    EccGeom g{ndens, mtot_log10, mrat, redz, dcom, gwfobs, sepa_evo, eccen_evo, M, Q, Z, F, E, H};
+    EccConsts cc{gw_dadt_sep_const, gw_src_const};
+    std::vector<double> frst_pref(E), bsum((size_t)Z * M);
+    for (int i = 0; i < E; ++i) frst_pref[i] = ((1.0 / (2.0 * CY_PI)) * sqrt(CY_NWTG)) / pow(sepa_evo[i], 1.5);
+    const double four_pi_c_mpc = 4 * CY_PI * (CY_SPLC / CY_MPC);
+    for (int kk = 0; kk < Z; ++kk)
+        for (int ii = 0; ii < M; ++ii) {
+            double kw, kdx, iw, idx_;
+            trapz_grid_weight(kk, Z, redz, &kw, &kdx);
+            trapz_grid_weight(ii, M, mtot_log10, &iw, &idx_);
+            const double zterm = 1.0 + redz[kk], dc_mpc = dcom[kk], dc_cm = dc_mpc * CY_MPC;
+            const double dc_term = four_pi_c_mpc * pow(dc_mpc, 2.0);
+            const double mt = pow(10.0, mtot_log10[ii]);
+            const double weight_ik = idx_ * kdx / (iw * kw);
+            double acc = 0.0;
+            for (int jj = 0; jj < Q; ++jj) {
+                double jw, jdx;
+                trapz_grid_weight(jj, Q, mrat, &jw, &jdx);
+                const double weight = weight_ik * (jdx / jw);
+                const double q = mrat[jj], m1 = mt / (1.0 + q), m2 = mt - m1;
+                const double mchirp = mt * pow(q, 3.0 / 5.0) / pow(1 + q, 6.0 / 5.0);
+                double hp = ndens[((int64_t)ii * Q + jj) * Z + kk] * dc_term * zterm;
+                hp *= pow(gw_src_const * mchirp * pow(2.0 * mchirp, 2.0 / 3.0) / dc_cm, 2.0);
+                acc += weight * hp / (m1 * m2);
+            }
+            bsum[(size_t)kk * M + ii] = acc;
+        }
+    for (int ff = 0; ff < F; ++ff)
+        for (int nh = 1; nh <= H; ++nh) {
+            double acc = 0.0;
+            for (int p = 0; p < Z * M; ++p) {
+                if (bsum[p] == 0.0) continue;
+                double afac, tf, hf;
+                if (eccen_factor(g, cc, frst_pref.data(), p / M, p % M, ff, nh, &afac, &tf, &hf)) acc += afac * bsum[p];
+            }
+            gwb[(size_t)ff * H + nh - 1] = acc;
+        }
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+"""CPU tests of the host-side mirror of the reference API (no kernels are launched)."""
+import numpy as np
+import pytest
+
+import holodeck_b200 as holo
+from holodeck_b200 import utils, sams, host_relations, hardening
+from holodeck_b200.constants import MSOL, YR, GYR
+
+
+def test_semi_analytic_model_grid_and_components():
+    sam = sams.Semi_Analytic_Model()
+    assert sam.shape == (91, 81, 101)
+    assert np.isclose(sam.mtot[0], 1e4 * MSOL) and np.isclose(sam.mtot[-1], 1e12 * MSOL)
+    assert np.isclose(sam.mrat[0], 1e-3) and sam.mrat[-1] == 1.0 and np.isclose(sam.redz[-1], 10.0)
+    # gpf=None -> GMR_Illustris and no GMT (sam.py:168-174)
+    assert isinstance(sam._gmr, sams.GMR_Illustris) and sam._gpf is None and sam._gmt is None
+    assert isinstance(sam._mmbulge, host_relations.MMBulge_KH2013)
+    sam2 = sams.Semi_Analytic_Model(gpf=sams.GPF_Power_Law, shape=(7, None, 9))
+    assert sam2.shape == (7, 81, 9) and isinstance(sam2._gmt, sams.GMT_Power_Law) and sam2._gmr is None
+    with pytest.raises(ValueError):
+        sams.Semi_Analytic_Model(gpf=sams.GPF_Power_Law, gmr=sams.GMR_Illustris)
+    with pytest.raises(ValueError):
+        sams.Semi_Analytic_Model(bogus=1)
+    with pytest.raises(ValueError):
+        sams.Semi_Analytic_Model(gsmf=object())
+    mstar_pri, mstar_rat, mstar_tot, redz = sam2.mass_stellar()
+    assert mstar_pri.shape == sam2.shape and np.all(mstar_rat <= 1.0 + 1e-12) and np.all(mstar_tot >= mstar_pri)
+
+
+def test_components_are_callable_like_the_reference():
+    """sams/tests/test_components.py:52-133 -- every component evaluates on random inputs."""
+    rng = np.random.default_rng(0)
+    mstar = 10.0 ** rng.uniform(9, 12, 50) * MSOL
+    mrat = 10.0 ** rng.uniform(-2, 0, 50)
+    redz = rng.uniform(0, 5, 50)
+    for gsmf in (sams.GSMF_Schechter(), sams.GSMF_Double_Schechter()):
+        vals = gsmf(mstar, redz)
+        assert vals.shape == mstar.shape and np.all(vals > 0)
+    assert np.all(sams.GPF_Power_Law()(mstar, mrat, redz) <= 1.0)
+    assert np.all(sams.GMT_Power_Law()(mstar, mrat, redz) > 0)
+    assert np.all(sams.GMR_Illustris()(mstar, mrat, redz) > 0)
+    with pytest.raises(TypeError):
+        sams.components._Galaxy_Stellar_Mass_Function()
+    with pytest.raises(ValueError):
+        sams.GPF_Power_Law(max_frac=1.5)
+    zp, tau = sams.GMT_Power_Law().zprime(mstar, mrat, redz)
+    assert np.all((zp < redz) | (zp == -1.0)) and np.all(tau > 0)
+    # frac_norm from frac_norm_allq (components.py:532-539)
+    gpf = sams.GPF_Power_Law(frac_norm_allq=0.03, qgamma=0.5)
+    assert np.isclose(gpf._frac_norm, 0.03 / ((1.0 - 0.25**1.5) / 1.5))
+
+
+def test_unfusable_components_are_rejected_not_emulated():
+    class MyGSMF(sams.GSMF_Schechter):
+        def __call__(self, mstar, redz):
+            return np.ones_like(mstar)
+    sam = sams.Semi_Analytic_Model(gsmf=MyGSMF, shape=6)
+    with pytest.raises(NotImplementedError):
+        sam._kernel_params()
+    ok = sams.Semi_Analytic_Model(gsmf=sams.GSMF_Double_Schechter, gpf=sams.GPF_Power_Law, shape=6)._kernel_params()
+    assert ok.gsmf_kind == 1 and ok.use_gmr == 0 and ok.has_gmt == 1 and ok.mmb[1] == 1.17
+
+
+def test_pta_freqs_and_utils():
+    cents, edges = utils.pta_freqs(16.03 * YR, 40)
+    assert cents.size == 40 and edges.size == 41
+    assert np.allclose(cents, np.arange(1, 41) / (16.03 * YR)) and np.allclose(utils.midpoints(edges), cents)
+    assert utils.isinteger(5) and utils.isinteger(np.int64(5)) and not utils.isinteger(5.0)
+    m1, m2 = utils.m1m2_from_mtmr(10.0, 0.25)
+    assert np.isclose(m1, 8.0) and np.isclose(m2, 2.0)
+    assert utils.redz_after(1e30, redz=1.0) == -1.0
+    zz = utils.redz_after(np.array([0.0, 1.0 * GYR]), redz=np.array([1.0, 1.0]))
+    assert np.isclose(zz[0], 1.0) and 0 < zz[1] < 1.0
+    with pytest.raises(ValueError):
+        utils.redz_after(1.0)
+    assert utils.get_subclass_instance(None, sams.GSMF_Schechter, sams.components._Galaxy_Stellar_Mass_Function) is not None
+    with pytest.raises(ValueError):
+        utils.get_subclass_instance(3, None, sams.components._Galaxy_Stellar_Mass_Function)
+
+
+def test_hard_gw_and_gwb_ideal_host_paths():
+    dadt = hardening.Hard_GW.dadt(1e9 * MSOL, 0.5, 3.0e16)
+    assert dadt < 0
+    assert hardening.Hard_GW.deda(1e17, 0.5) > 0
+    with pytest.raises(NotImplementedError):
+        sams.Semi_Analytic_Model(shape=5).dynamic_binary_number_at_fobs(hardening.Hard_GW(), np.array([1e-9]), use_cython=False)
+
+
+def test_param_space_and_sharding():
+    from holodeck_b200 import librarian, dist
+    sp1 = librarian.PS_Classic_Phenom_Uniform(nsamples=16, sam_shape=9, seed=7)
+    sp2 = librarian.PS_Classic_Phenom_Uniform(nsamples=16, sam_shape=9, seed=7)
+    assert np.array_equal(sp1.param_samples, sp2.param_samples) and sp1.param_samples.shape == (16, 6)
+    # latin hypercube: one sample per stratum in each dimension
+    strata = np.sort(np.floor(sp1._uniform_samples * 16), axis=0)
+    assert np.array_equal(strata, np.tile(np.arange(16.0)[:, None], (1, 6)))
+    lo, hi = sp1.extrema[:, 0], sp1.extrema[:, 1]
+    assert np.all(sp1.param_samples >= lo) and np.all(sp1.param_samples <= hi)
+    assert set(sp1.default_params()) == set(sp1.param_names)
+    pp = sp1.normalized_params(0.5)
+    assert np.isclose(pp["hard_time"], 5.55)
+    # sample sharding: a partition of all samples, identical on every rank
+    parts = [dist.sample_indices(37, seed=3, rank=rr, size=4) for rr in range(4)]
+    assert sorted(np.concatenate(parts).tolist()) == list(range(37)) and max(map(len, parts)) - min(map(len, parts)) <= 1
+    slices = [dist.realization_slice(1000, rr, 8) for rr in range(8)]
+    assert slices[0] == (0, 125) and slices[-1] == (875, 125)
+    ragged = [dist.realization_slice(10, rr, 4) for rr in range(4)]
+    assert [ss[1] for ss in ragged] == [3, 3, 2, 2] and [ss[0] for ss in ragged] == [0, 3, 6, 8]
+    ext = librarian.PS_Classic_Phenom_Astro_Extended(nsamples=4, seed=1)
+    assert ext.param_names[2] == "gsmf_phi0_log10"     # renamed from `gsmf_phi0` (lib_tools.py:24-26)
+    with pytest.raises(RuntimeError):
+        librarian.run_model(None, None, gwb_flag=False, singles_flag=False)

@@ -1,0 +1,171 @@
+"""CPU tests of the kernels' per-element math (holodeck_b200/csrc/*.cuh compiled for the host by
+tests/hostemu) against the golden fixtures, i.e. against the compiled reference.  This checks the
+arithmetic the CUDA kernels run -- not the launch machinery, which the `-m gpu` tests cover."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import rel_err, load_golden
+from _stubs import edges_orb
+
+HERE = Path(__file__).resolve().parent
+SO = HERE / "hostemu" / "libhostemu.so"
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = HERE / "hostemu" / "hostemu.cpp"
+    if (not SO.exists()) or SO.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(SO), str(src)], check=True)
+    return C.CDLL(str(SO))
+
+
+def P(arr):
+    return None if arr is None else arr.ctypes.data_as(C.c_void_p)
+
+
+def test_emu_norm_and_dbn(emu, golden):
+    from holodeck_b200 import _lib as L
+    gg = golden
+    cc = L.cy_consts()
+    M, Q, Z = gg["mtot"].size, gg["mrat"].size, gg["redz"].size
+    fo = np.ascontiguousarray(gg["fobs_cents"] / 2.0)
+    F = fo.size
+    rz = np.zeros((M, Q, Z, F))
+    dn = np.zeros((M, Q, Z, F))
+    if str(gg["hard"]) == "2pwl":
+        hp = gg["hard_params"]
+        mt, mr = np.meshgrid(gg["mtot"], gg["mrat"], indexing="ij")
+        mt, mr = np.ascontiguousarray(mt.flatten()), np.ascontiguousarray(mr.flatten())
+        out = np.zeros(M * Q)
+        emu.emu_norm_2pwl.argtypes = [L.CyConsts, C.c_double, C.c_void_p, C.c_void_p, C.c_int] + [C.c_double] * 4 + \
+            [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        emu.emu_norm_2pwl(cc, hp[0], P(mt), P(mr), M * Q, hp[1], hp[2], hp[3], hp[4], int(hp[5]), 0, None, P(out))
+        assert np.max(np.abs(out - gg["norm_log10"].flatten())) < 1e-12
+        norm = np.ascontiguousarray(10.0 ** gg["norm_log10"])
+        emu.emu_dbn_2pwl.argtypes = [L.CyConsts, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p] + [C.c_double] * 3 + \
+            [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2
+        emu.emu_dbn_2pwl(cc, P(fo), F, hp[1], int(hp[5]), P(norm), hp[2], hp[3], hp[4], P(gg["dens"]), P(gg["mtot"]),
+                         P(gg["mrat"]), P(gg["redz"]), P(gg["gmt_time"]), M, Q, Z, P(gg["grid_z"]), P(gg["grid_dcom"]),
+                         P(gg["grid_age"]), gg["grid_z"].size, P(rz), P(dn))
+    else:
+        zp = gg["redz_prime"] if "redz_prime" in gg else np.ascontiguousarray(np.broadcast_to(gg["redz"], (M, Q, Z)))
+        emu.emu_dbn_gw.argtypes = [L.CyConsts, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p] * 2 + \
+            [C.c_int] + [C.c_void_p] * 2
+        emu.emu_dbn_gw(cc, P(fo), F, P(gg["dens"]), P(gg["mtot"]), P(gg["mrat"]), P(zp), M, Q, Z, P(gg["grid_z"]),
+                       P(gg["grid_dcom"]), gg["grid_z"].size, P(rz), P(dn))
+    assert np.array_equal(rz == -1, gg["redz_final"] == -1)
+    assert rel_err(rz, gg["redz_final"]) < 1e-13
+    assert np.array_equal(dn == 0, gg["diff_num"] == 0)
+    assert rel_err(dn, gg["diff_num"]) < 1e-12
+
+
+def test_emu_integrate_and_strain(emu, golden):
+    from holodeck_b200 import _lib as L, cosmo, utils
+    from holodeck_b200.constants import NWTG
+    gg = golden
+    edges = edges_orb(gg)
+    M, Q, Z = gg["mtot"].size, gg["mrat"].size, gg["redz"].size
+    F = gg["fobs_cents"].size
+    shape = (M - 1, Q - 1, Z - 1, F)
+    numb, h2, zm, dc, se, an = [np.zeros(shape) for _ in range(6)]
+    l10m = np.log10(edges[0])
+    dlnf = np.diff(np.log(edges[3]))
+    mtm, mrm = utils.midpoints(edges[0]), utils.midpoints(edges[1])
+    fc = utils.midpoints(edges[3])
+    fdf = fc / np.diff(edges[3])
+    cp = L.cosmo_params(cosmo)
+    emu.emu_integrate_and_strain.argtypes = [C.c_void_p, C.c_double, C.c_double] + [C.c_void_p] * 11 + [C.c_int] * 4 + [C.c_void_p] * 6
+    emu.emu_integrate_and_strain(C.byref(cp), utils._GW_SRC_CONST, NWTG, P(l10m), P(edges[1]), P(edges[2]), P(dlnf),
+                                 P(gg["diff_num"]), P(gg["redz_final"]), None, P(mtm), P(mrm), P(fc), P(fdf), M, Q, Z, F,
+                                 P(numb), P(h2), P(zm), P(dc), P(se), P(an))
+    assert np.array_equal(numb, gg["number"])
+    assert np.array_equal(h2 == 0, gg["h2fdf"] == 0)
+    assert rel_err(h2, gg["h2fdf"]) < 1e-12
+    assert np.max(np.abs(zm - gg["par_redz"])) < 1e-14
+    fin = np.isfinite(gg["par_dcom"])
+    assert np.array_equal(np.isfinite(dc), fin) and rel_err(dc[fin], gg["par_dcom"][fin]) < 1e-12
+    fin = np.isfinite(gg["par_angs"])
+    assert rel_err(an[fin], gg["par_angs"][fin]) < 1e-12 and rel_err(se[fin], gg["par_sepa"][fin]) < 1e-13
+
+
+def test_emu_density(emu, golden_classic):
+    from holodeck_b200 import _lib as L, cosmo, utils
+    from holodeck_b200.constants import MSOL, GYR
+    gg = golden_classic
+    M, Q, Z = gg["mtot"].size, gg["mrat"].size, gg["redz"].size
+    sp = L.SamParams()
+    sp.gsmf_kind, sp.use_gmr, sp.has_gmt = 0, 0, 1
+    for ii, vv in enumerate([-2.77, -0.6, MSOL * np.power(10.0, 11.24), 0.11, -1.21, -0.03]):
+        sp.gsmf[ii] = vv
+    for ii, vv in enumerate([0.025 / ((1.0 - 0.25) / 1.0), MSOL * np.power(10.0, 11.0), 0.0, 1.0, 0.0, 1.0]):
+        sp.gpf[ii] = vv
+    for ii, vv in enumerate([0.5 * GYR, 1.0e11 * MSOL * (0.4 / cosmo.h), 0.0, -0.5, -1.0]):
+        sp.gmt[ii] = vv
+    for ii, vv in enumerate([MSOL * np.power(10.0, 8.69), 1.10, 1.0e11 * MSOL, 0.615]):
+        sp.mmb[ii] = vv
+    sp.hubble_time, sp.om0, sp.age_universe = cosmo.hubble_time, cosmo.Om0, utils._AGE_UNIVERSE_GYR * GYR
+    dens, gt, zp = [np.zeros((M, Q, Z)) for _ in range(3)]
+    age_z, dtdz = cosmo.age(gg["redz"]), cosmo.dtdz(gg["redz"])
+    emu.emu_sam_density(P(gg["mtot"]), P(gg["mrat"]), P(gg["redz"]), P(age_z), P(dtdz), M, Q, Z, C.byref(sp), P(dens), P(gt), P(zp))
+    dens[zp < 0] = 0.0
+    assert np.array_equal(zp == -1, gg["redz_prime"] == -1)
+    assert rel_err(dens, gg["dens"]) < 1e-11
+    assert rel_err(gt, gg["gmt_time"]) < 1e-13
+
+
+def test_emu_samplers_are_exact_poisson(emu):
+    """Chi-square of the Philox/inversion/PTRS samplers against the exact pmf, every class."""
+    import scipy.stats as st
+    emu.emu_draw_elements.argtypes = [C.c_double, C.c_int64, C.c_uint64, C.c_double, C.c_uint64, C.c_void_p]
+    N = 300000
+    for ii, lam in enumerate([2e-3, 0.5, 4.0, 9.99, 10.0, 14.0, 80.0, 2.5e3, 7e5, 3e9]):
+        dd = np.zeros(N)
+        emu.emu_draw_elements(lam, N, 900 + ii, 1e10, 5 + ii, P(dd))
+        assert np.all(dd == np.floor(dd)) and np.all(dd >= 0)
+        assert abs(dd.mean() - lam) < 5.0 * np.sqrt(lam / N)
+        if lam >= 0.5:
+            lo, hi = int(st.poisson.ppf(1e-3, lam)), int(st.poisson.ppf(1 - 1e-3, lam)) + 1
+            nb = min(60, hi - lo + 1)
+            edges = np.unique(np.linspace(lo, hi + 1, nb + 1).astype(np.int64))     # bin i = [edges[i], edges[i+1])
+            which = np.searchsorted(edges, dd.astype(np.int64), side="right") - 1
+            inside = (dd >= edges[0]) & (dd < edges[-1])
+            obs = np.bincount(which[inside], minlength=edges.size - 1).astype(float)
+            exp = N * (st.poisson.cdf(edges[1:] - 1, lam) - st.poisson.cdf(edges[:-1] - 1, lam))
+            sel = exp > 20
+            chi2 = np.sum((obs[sel] - exp[sel])**2 / exp[sel])
+            assert st.chi2.sf(chi2, sel.sum()) > 1e-4, (lam, chi2, sel.sum())
+    # the normal branch (lam > thresh) is not floored
+    dd = np.zeros(20000)
+    emu.emu_draw_elements(5e10, 20000, 1, 1e10, 0, P(dd))
+    assert np.any(dd != np.floor(dd)) and abs(dd.mean() / 5e10 - 1) < 1e-7 and abs(dd.std() / np.sqrt(5e10) - 1) < 0.03
+
+
+def test_emu_philox_known_answers(emu):
+    """Random123 known-answer vectors for Philox4x32-10."""
+    emu.emu_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
+    out = np.zeros(4, dtype=np.uint32)
+    emu.emu_philox(0, 0, 0, 0, 0, 0, P(out))
+    assert [int(vv) for vv in out] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    emu.emu_philox(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, P(out))
+    assert [int(vv) for vv in out] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    emu.emu_philox(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0, P(out))
+    assert [int(vv) for vv in out] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_emu_eccentric_gwb(emu):
+    from holodeck_b200 import _lib as L
+    gg = load_golden("eccen_small")
+    M, Q, Z, F, H = gg["mtot"].size, gg["mrat"].size, gg["redz"].size, gg["fobs"].size, int(gg["nharms"])
+    l10 = np.log10(gg["mtot"])
+    emu.emu_eccen_gwb.argtypes = [C.c_double, C.c_double] + [C.c_void_p] * 8 + [C.c_int] * 6 + [C.c_void_p]
+    for tag, tol in (("a", 1e-12), ("b", 1e-8)):
+        out = np.zeros((F, H))
+        sepa, ecc = gg[f"sepa_{tag}"], gg[f"eccen_{tag}"]
+        emu.emu_eccen_gwb(L.cy_consts().gw_dadt_sep_const, L.cy_gw_src_const(), P(gg["ndens"]), P(l10), P(gg["mrat"]),
+                          P(gg["redz"]), P(gg["dcom"]), P(gg["fobs"]), P(sepa), P(ecc), M, Q, Z, F, sepa.size, H, P(out))
+        assert np.array_equal(out == 0, gg[f"gwb_{tag}"] == 0)
+        assert rel_err(out, gg[f"gwb_{tag}"]) < tol
