@@ -11,7 +11,7 @@ from pathlib import Path
 
 import numpy as np
 
-GL_ORDER = 24
+GL_ORDER = 16
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libholo_b200.so"

@@ -23,7 +23,7 @@ import numpy as np
 
 from .constants import MPC, KMPERSEC, SPLC, GYR
 
-GL_ORDER = 24   #: Gauss-Legendre order of the comoving-distance quadrature (host and device)
+GL_ORDER = 16   #: Gauss-Legendre order of the comoving-distance quadrature (host and device)
 
 _GL_X, _GL_W = np.polynomial.legendre.leggauss(GL_ORDER)
 

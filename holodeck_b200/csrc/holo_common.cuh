@@ -116,7 +116,7 @@ HOLO_HD double hard_func_2pwl_gw(const CyConsts& cc, double mtot, double mrat, d
 }
 
 // ---- flat-LCDM comoving distance (host twin: holodeck_b200/cosmology.py:comoving_distance) -----
-constexpr int GL_ORDER = 24;
+constexpr int GL_ORDER = 16;
 
 struct GLTable {
     double x[GL_ORDER];

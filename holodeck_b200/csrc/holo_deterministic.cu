@@ -103,18 +103,23 @@ norm_2pwl_kernel(CyConsts cc, double target_time, const double* __restrict__ mto
     double mt = mtot[i], mr = mrat[i];
     double risco_log10 = log10(3.0 * CY_SCHW * mt);                      // pyx:363
     double dx = (sepa_init_log10 - risco_log10) / nsteps;               // pyx:368
-    // every lane walks the same `sepa_log10 -= dx` chain (pyx:381) and keeps its own steps
-    double slog = sepa_init_log10;
-    for (int k = 0; k < ne; ++k) {
-        if ((k & 31) == lane) {
-            double sp = pow(10.0, slog);
-            double xx = sp / rchar;
-            sepa[k] = sp;
-            p1[k] = pow(1.0 + xx, -gamma_outer + gamma_inner);          // pyx:242
-            p2[k] = pow(xx, gamma_inner - 1.0);
-            gw[k] = hard_gw(cc, mt, mr, sp);
+    // the running `sepa_log10 -= dx` of the reference (pyx:381) is kept serial so it rounds identically:
+    // lane 0 walks the chain once into shared memory, then the lanes share the transcendental work
+    if (lane == 0) {
+        double slog = sepa_init_log10;
+        for (int k = 0; k < ne; ++k) {
+            sepa[k] = slog;
+            slog -= dx;
         }
-        slog -= dx;
+    }
+    __syncwarp();
+    for (int k = lane; k < ne; k += 32) {
+        const double sp = pow(10.0, sepa[k]);
+        const double xx = sp / rchar;
+        sepa[k] = sp;
+        p1[k] = pow(1.0 + xx, -gamma_outer + gamma_inner);              // pyx:242
+        p2[k] = pow(xx, gamma_inner - 1.0);
+        gw[k] = hard_gw(cc, mt, mr, sp);
     }
     __syncwarp();
     NormTrack t{sepa, p1, p2, gw, nsteps};
@@ -262,51 +267,51 @@ dbn_gw_kernel(CyConsts cc, const double* __restrict__ fobs, int F, const double*
 // -------------------------------------------------------------------------------------------------
 // K2 / K2b / fused
 // -------------------------------------------------------------------------------------------------
-__global__ void chirp_table_kernel(const double* __restrict__ mt_mid, const double* __restrict__ mr_mid,
-                                   int Mb, int Qb, double* __restrict__ mc) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < Mb * Qb) mc[i] = chirp_mass_mtmr(mt_mid[i / Qb], mr_mid[i % Qb]);
-}
-
 struct BinGeom {
     int M, Q, Z, F;   // edge counts
 };
 
+// One CTA per (m,q) bin; its threads sweep the (z,f) plane, f fastest (coalesced 8-corner stencils).
+// All index arithmetic is 32-bit; only the final address is 64-bit.
 template <bool DO_NUM, bool DO_STRAIN>
 __global__ void __launch_bounds__(256)
 bin_kernel(BinGeom g, GLTable gl, double hubble_distance, double om0, double gw_src_const, double nwtg,
            const double* __restrict__ log10_mtot, const double* __restrict__ mrat,
            const double* __restrict__ redz, const double* __restrict__ dln_freq,
            const double* __restrict__ dnum, const double* __restrict__ redz_final,
-           const double* __restrict__ rz_mid, const double* __restrict__ mc_tab,
-           const double* __restrict__ mt_mid, const double* __restrict__ fc,
+           const double* __restrict__ rz_mid, const double* __restrict__ mt_mid,
+           const double* __restrict__ mr_mid, const double* __restrict__ fc,
            const double* __restrict__ fc_over_df, double* __restrict__ numb,
            double* __restrict__ h2fdf, double* __restrict__ zmid, double* __restrict__ dcom,
            double* __restrict__ sepa, double* __restrict__ angs) {
-    int Mb = g.M - 1, Qb = g.Q - 1, Zb = g.Z - 1, F = g.F;
-    int64_t n = (int64_t)Mb * Qb * Zb * F;
-    int64_t sZ = F, sQ = (int64_t)g.Z * F, sM = (int64_t)g.Q * g.Z * F;
-    bool want_par = (zmid != nullptr) || (dcom != nullptr) || (sepa != nullptr) || (angs != nullptr);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int ff = (int)(i % F);
-        int64_t c = i / F;
-        int zz = (int)(c % Zb);
-        int64_t mq = c / Zb;
-        int qq = (int)(mq % Qb);
-        int mm = (int)(mq / Qb);
-        int64_t base = mm * sM + qq * sQ + zz * sZ + ff;
+    const int Qb = g.Q - 1, Zb = g.Z - 1, F = g.F;
+    const int mm = blockIdx.x / Qb, qq = blockIdx.x - mm * Qb;
+    const int64_t sZ = F, sQ = (int64_t)g.Z * F, sM = (int64_t)g.Q * g.Z * F;
+    const bool want_par = (zmid != nullptr) || (dcom != nullptr) || (sepa != nullptr) || (angs != nullptr);
+    const int64_t in0 = mm * sM + qq * sQ;                      // first edge element of this (m,q)
+    const int64_t out0 = (int64_t)blockIdx.x * Zb * F;         // first bin element of this (m,q)
+    double dmdq = 0.0, mc = 0.0, mtm = 0.0;
+    if (DO_NUM) {
+        const double dm = log10_mtot[mm + 1] - log10_mtot[mm];          // pyx:195
+        dmdq = dm * (mrat[qq + 1] - mrat[qq]);                          // pyx:198
+    }
+    if (DO_STRAIN) {
+        mtm = mt_mid[mm];
+        mc = chirp_mass_mtmr(mtm, mr_mid[qq]);
+    }
+    const int nzf = Zb * F;
+    for (int zf = threadIdx.x; zf < nzf; zf += blockDim.x) {
+        const int zz = zf / F, ff = zf - zz * F;
+        const int64_t base = in0 + zz * sZ + ff;
+        const int64_t i = out0 + zf;
         if (DO_NUM) {
-            double dm = log10_mtot[mm + 1] - log10_mtot[mm];             // pyx:195
-            double dmdq = dm * (mrat[qq + 1] - mrat[qq]);                // pyx:198
-            double dmdqdz = dmdq * (redz[zz + 1] - redz[zz]);            // pyx:201
+            const double dmdqdz = dmdq * (redz[zz + 1] - redz[zz]);      // pyx:201
             numb[i] = integrate_bin(dnum, sM, sQ, sZ, base, dmdqdz, dln_freq[ff]);
         }
         if (DO_STRAIN) {
-            double zc = redz_final ? corner_mean_redz(redz_final, sM, sQ, sZ, base) : rz_mid[zz];
-            StrainOut o = strain_cell(gl, hubble_distance, om0, gw_src_const, nwtg, zc,
-                                      mc_tab[mm * Qb + qq], mt_mid[mm], fc[ff], fc_over_df[ff],
-                                      want_par);
+            const double zc = redz_final ? corner_mean_redz(redz_final, sM, sQ, sZ, base) : rz_mid[zz];
+            const StrainOut o = strain_cell(gl, hubble_distance, om0, gw_src_const, nwtg, zc, mc, mtm, fc[ff],
+                                            fc_over_df[ff], want_par);
             h2fdf[i] = o.h2fdf;
             if (zmid) zmid[i] = o.zmid;
             if (dcom) dcom[i] = o.dcom;
@@ -475,7 +480,7 @@ int holo_integrate_differential_number_3dx1d(const double* log10_mtot, const dou
     if (n <= 0) return HOLO_OK;
     BinGeom g{M, Q, Z, F};
     GLTable gl{};
-    bin_kernel<true, false><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+    bin_kernel<true, false><<<(M - 1) * (Q - 1), 256, 0, (cudaStream_t)stream>>>(
         g, gl, 0, 0, 0, 0, log10_mtot, mrat, redz, dln_freq, dnum, nullptr, nullptr, nullptr, nullptr,
         nullptr, nullptr, numb, nullptr, nullptr, nullptr, nullptr, nullptr); holo::count_launches(1);
     return holo_check_launch("holo_integrate_differential_number_3dx1d");
@@ -487,15 +492,6 @@ static GLTable to_gl(const holo_cosmo_params* c) {
     return gl;
 }
 
-// scratch for the (Mb*Qb) chirp-mass table lives at the head of h2fdf's last row?  No: keep it
-// simple and stream-ordered.
-static int chirp_table(const double* mt_mid, const double* mr_mid, int Mb, int Qb, double** mc,
-                       cudaStream_t st) {
-    HOLO_CUDA(cudaMallocAsync((void**)mc, sizeof(double) * (size_t)Mb * Qb, st));
-    chirp_table_kernel<<<(Mb * Qb + 255) / 256, 256, 0, st>>>(mt_mid, mr_mid, Mb, Qb, *mc); holo::count_launches(1);
-    return holo_check_launch("chirp_table");
-}
-
 int holo_char_strain_sq(const holo_cosmo_params* cosmo, double gw_src_const, double nwtg,
                         const double* redz_final, const double* rz_mid, const double* mt_mid,
                         const double* mr_mid, const double* fc, const double* fc_over_df, int M,
@@ -505,18 +501,12 @@ int holo_char_strain_sq(const holo_cosmo_params* cosmo, double gw_src_const, dou
                  "holo_char_strain_sq: NULL argument");
     HOLO_REQUIRE(M > 1 && Q > 1 && Z > 1 && F > 0, "holo_char_strain_sq: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
-    int64_t n = (int64_t)(M - 1) * (Q - 1) * (Z - 1) * F;
-    double* mc = nullptr;
-    int rc = chirp_table(mt_mid, mr_mid, M - 1, Q - 1, &mc, st);
-    if (rc) return rc;
     BinGeom g{M, Q, Z, F};
-    bin_kernel<false, true><<<grid_for(n, 256), 256, 0, st>>>(
+    bin_kernel<false, true><<<(M - 1) * (Q - 1), 256, 0, st>>>(
         g, to_gl(cosmo), cosmo->hubble_distance, cosmo->om0, gw_src_const, nwtg, nullptr, nullptr,
-        nullptr, nullptr, nullptr, redz_final, rz_mid, mc, mt_mid, fc, fc_over_df, nullptr, h2fdf,
+        nullptr, nullptr, nullptr, redz_final, rz_mid, mt_mid, mr_mid, fc, fc_over_df, nullptr, h2fdf,
         zmid, dcom, sepa, angs); holo::count_launches(1);
-    rc = holo_check_launch("holo_char_strain_sq");
-    cudaFreeAsync(mc, st);
-    return rc;
+    return holo_check_launch("holo_char_strain_sq");
 }
 
 int holo_integrate_and_strain(const holo_cosmo_params* cosmo, double gw_src_const, double nwtg,
@@ -530,18 +520,12 @@ int holo_integrate_and_strain(const holo_cosmo_params* cosmo, double gw_src_cons
                  mr_mid && fc && fc_over_df && numb && h2fdf, "holo_integrate_and_strain: NULL argument");
     HOLO_REQUIRE(M > 1 && Q > 1 && Z > 1 && F > 0, "holo_integrate_and_strain: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
-    int64_t n = (int64_t)(M - 1) * (Q - 1) * (Z - 1) * F;
-    double* mc = nullptr;
-    int rc = chirp_table(mt_mid, mr_mid, M - 1, Q - 1, &mc, st);
-    if (rc) return rc;
     BinGeom g{M, Q, Z, F};
-    bin_kernel<true, true><<<grid_for(n, 256), 256, 0, st>>>(
+    bin_kernel<true, true><<<(M - 1) * (Q - 1), 256, 0, st>>>(
         g, to_gl(cosmo), cosmo->hubble_distance, cosmo->om0, gw_src_const, nwtg, log10_mtot, mrat, redz,
-        dln_freq, dnum, redz_final, nullptr, mc, mt_mid, fc, fc_over_df, numb, h2fdf, zmid, dcom,
+        dln_freq, dnum, redz_final, nullptr, mt_mid, mr_mid, fc, fc_over_df, numb, h2fdf, zmid, dcom,
         sepa, angs); holo::count_launches(1);
-    rc = holo_check_launch("holo_integrate_and_strain");
-    cudaFreeAsync(mc, st);
-    return rc;
+    return holo_check_launch("holo_integrate_and_strain");
 }
 
 int holo_gwb_expectation(const double* number, const double* h2fdf, int64_t ncell, int F, double* hc2,

@@ -326,21 +326,26 @@ HOLO_HD StrainOut strain_cell(const GLTable& gl, double hubble_distance, double 
                               double gw_src_const, double nwtg, double zc, double mc, double mt_mid,
                               double fc, double fc_over_df, bool want_params) {
     StrainOut o;
-    double inf = 1.0 / 0.0;
-    bool sel = (zc > 0.0);
-    double dc = sel ? comoving_distance_cm(gl, hubble_distance, om0, zc) : inf;
-    double fr = fc * (1.0 + zc);                                       // utils.frst_from_fobs
-    // utils.gw_strain_source utils.py:2260-2285
-    double hs = gw_src_const * mc * pow(2.0 * mc * fr, 2.0 / 3.0) / dc;
-    o.h2fdf = (hs * hs) * fc_over_df;                                  // gravwaves.py:723
+    const double inf = 1.0 / 0.0;
+    const bool sel = (zc > 0.0);
+    const double dc = sel ? comoving_distance_cm(gl, hubble_distance, om0, zc) : inf;
+    double h2 = 0.0;
+    if (sel) {
+        const double fr = fc * (1.0 + zc);                               // utils.frst_from_fobs
+        // utils.gw_strain_source utils.py:2260-2285; x^(2/3) as cbrt(x)^2 (|diff| to pow <= 2 ulp)
+        const double cb = cbrt(2.0 * mc * fr);
+        const double hs = gw_src_const * mc * (cb * cb) / dc;
+        h2 = (hs * hs) * fc_over_df;                                     // gravwaves.py:723
+    }
+    o.h2fdf = h2;                                                        // z <= 0: d_c = inf -> hs = 0
     o.zmid = zc; o.dcom = dc; o.sepa = 0.0; o.angs = 0.0;
     if (want_params) {
         // single_sources.py:124-139
-        double rz = sel ? zc : -1.0;
-        double frp = fc * (1.0 + rz);
-        double two_pi_f = 2.0 * CY_PI * frp;
-        double sepa = pow(nwtg * mt_mid / (two_pi_f * two_pi_f), 1.0 / 3.0);   // utils.py:1705-1724
-        double dang = dc / (1.0 + rz);                                         // utils.py:1897-1917
+        const double rz = sel ? zc : -1.0;
+        const double frp = fc * (1.0 + rz);
+        const double two_pi_f = 2.0 * CY_PI * frp;
+        const double sepa = cbrt(nwtg * mt_mid / (two_pi_f * two_pi_f));   // utils.py:1705-1724 (1/0 -> inf for rz = -1)
+        const double dang = dc / (1.0 + rz);                             // utils.py:1897-1917
         o.zmid = rz; o.sepa = sepa; o.angs = sepa / dang;
     }
     return o;

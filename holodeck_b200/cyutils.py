@@ -29,6 +29,9 @@ __all__ = [
 
 _MAX_RETRY = 5
 
+#: diagnostics: how often `holo_loudest` had to be re-run with a larger head margin / event bucket
+STATS = {"loudest_calls": 0, "loudest_retries": 0}
+
 
 def _seed(seed):
     if seed is None:
@@ -155,8 +158,10 @@ def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, norm
         args.workspace = ws.data_ptr()
         args.workspace_bytes = ws.numel()
         rc = lib.holo_loudest(C.byref(args), _lib.stream())
+        STATS["loudest_calls"] += 1
         if rc != 3:
             break
+        STATS["loudest_retries"] += 1
         # bucket overflow / head too short (HOLO_ERR_OVERFLOW): enlarge both and redo the draws
         margin = (8.0 * np.sqrt(L) + 24.0) * (4.0 ** (attempt + 1))
         cap = min(2048, 256 * (2 ** (attempt + 1)))

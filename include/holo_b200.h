@@ -61,7 +61,7 @@ typedef struct {
 
 /* Flat-LCDM parameters + Gauss-Legendre nodes for the comoving-distance quadrature (the host twin
  * is holodeck_b200/cosmology.py; replaces astropy `cosmo.comoving_distance`, gravwaves.py:718). */
-#define HOLO_GL_ORDER 24
+#define HOLO_GL_ORDER 16
 typedef struct {
     double hubble_distance; /* c/H0 [cm] */
     double hubble_time;     /* 1/H0 [s]  */
