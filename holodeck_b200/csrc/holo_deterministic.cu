@@ -224,6 +224,7 @@ dbn_2pwl_kernel(CyConsts cc, const double* __restrict__ fobs, int F, double sepa
     t.tage = s_tage; t.gz = s_gz; t.gdc = s_gdc; t.n_interp = n_interp;
     t.age_universe = s_tage[n_interp - 1];                               // pyx:579
 
+    const MqConsts mqc = mq_consts(cc, mt, mr);
     int64_t base = (int64_t)mq * Z;
     int nzf = Z * F;
     for (int idx = tid; idx < nzf; idx += DBN_THREADS) {
@@ -231,7 +232,7 @@ dbn_2pwl_kernel(CyConsts cc, const double* __restrict__ fobs, int F, double sepa
         double rz = -1.0, dn = 0.0;                                      // pyx:460-461
         double gmt = gmt_time[base + kk];
         double nd = nden[base + kk];
-        dbn_2pwl_cell(cc, t, mt, mr, norm, rchar, gamma_inner, gamma_outer, nd, gmt, s_zage[kk],
+        dbn_2pwl_cell(cc, mqc, t, norm, rchar, gamma_inner, gamma_outer, nd, gmt, s_zage[kk],
                       s_fobs[ff], &rz, &dn);
         int64_t o = (base + kk) * F + ff;
         redz_final[o] = rz;

@@ -189,6 +189,32 @@ HOLO_HD double brentq(const Fn& f, double xa, double xb, double xtol, double rto
 // tevo[s] = cumulative evolution time at edge s (tevo[0] = 0), dt[s] = duration of step s.
 // =================================================================================================
 
+// Per-(M,q) factors of the Kepler / GW-hardening formulas, hoisted out of the per-(z,f) evaluation with the
+// reference's association order kept (sam_cyutils.pyx:48, 60); x^3 and f^(2/3) are formed by
+// multiplication / cbrt (<= 2 ulp from libm pow).
+struct MqConsts {
+    double kep_sepa_m;   // KEPLER_CONST_SEPA * pow(mtot, 1/3)
+    double gw_num;       // GW_DADT_SEP_CONST * pow(mtot, 3) * mrat
+    double opmr2;        // pow(1 + mrat, 2)
+};
+
+HOLO_HD MqConsts mq_consts(const CyConsts& cc, double mt, double mr) {
+    MqConsts k;
+    k.kep_sepa_m = cc.kepler_const_sepa * pow(mt, 1.0 / 3.0);
+    k.gw_num = cc.gw_dadt_sep_const * pow(mt, 3.0) * mr;
+    k.opmr2 = pow(1.0 + mr, 2.0);
+    return k;
+}
+
+HOLO_HD double kepler_sepa_fast(const MqConsts& k, double freq) {
+    const double cb = cbrt(freq);
+    return k.kep_sepa_m / (cb * cb);
+}
+
+HOLO_HD double hard_gw_fast(const MqConsts& k, double sepa) {
+    return k.gw_num / (sepa * sepa * sepa) / k.opmr2;
+}
+
 struct Track2pwl {
     const double* frst;   // (nsteps+1,)
     const double* tevo;   // (nsteps+1,)
@@ -213,7 +239,7 @@ HOLO_HD double fobs_right_of_step(const Track2pwl& t, int s, double gmt, double 
 
 // Returns true (and fills redz/dnum) iff some integration step brackets `ftarget`; when several do
 // (exact ties at step boundaries) the LAST one wins, as in the reference's step-major loop order.
-HOLO_HD bool dbn_2pwl_cell(const CyConsts& cc, const Track2pwl& t, double mt, double mr, double norm,
+HOLO_HD bool dbn_2pwl_cell(const CyConsts& cc, const MqConsts& mq, const Track2pwl& t, double norm,
                            double rchar, double gamma_inner, double gamma_outer, double nden,
                            double gmt, double age_z, double ftarget, double* redz_out,
                            double* dnum_out) {
@@ -244,10 +270,11 @@ HOLO_HD bool dbn_2pwl_cell(const CyConsts& cc, const Track2pwl& t, double mt, do
         double new_redz = interp_at_index(in, new_time, t.tage, t.gz);
         double dcom = interp_at_index(in, new_time, t.tage, t.gdc);
         double target_frst_orb = ftarget * (1.0 + new_redz);           // pyx:754
-        double sepa = kepler_sepa_from_freq(cc, mt, target_frst_orb);
-        double dadt = hard_func_2pwl_gw(cc, mt, mr, sepa, norm, rchar, gamma_inner, gamma_outer);
+        double sepa = kepler_sepa_fast(mq, target_frst_orb);
+        double dadt = hard_func_2pwl(norm, sepa / rchar, gamma_inner, gamma_outer) + hard_gw_fast(mq, sepa);
         double tres = -(2.0 / 3.0) * sepa / dadt;                      // pyx:764
-        double cosmo_fact = cc.four_pi_c_over_mpc * (1.0 + new_redz) * pow(dcom / CY_MPC, 2.0);
+        const double dmpc = dcom / CY_MPC;
+        double cosmo_fact = cc.four_pi_c_over_mpc * (1.0 + new_redz) * (dmpc * dmpc);
         *redz_out = new_redz;
         *dnum_out = nden * tres * cosmo_fact;                          // pyx:768
         found = true;
@@ -276,10 +303,12 @@ HOLO_HD void dbn_gw_cell(const CyConsts& cc, double mt, double mr, double nden, 
     if (target_frst_orb > frst_orb_isco) return;
     int idx = bracket_decreasing(n_interp, rzp, gz);                   // pyx:885
     double dcom = interp_at_index(idx, rzp, gz, gdc);
-    double sepa = kepler_sepa_from_freq(cc, mt, target_frst_orb);
-    double dadt = hard_gw(cc, mt, mr, sepa);
+    const MqConsts mq = mq_consts(cc, mt, mr);
+    double sepa = kepler_sepa_fast(mq, target_frst_orb);
+    double dadt = hard_gw_fast(mq, sepa);
     double tres = -(2.0 / 3.0) * sepa / dadt;
-    double cosmo_fact = cc.four_pi_c_over_mpc * (1.0 + rzp) * pow(dcom / CY_MPC, 2.0);
+    const double dmpc = dcom / CY_MPC;
+    double cosmo_fact = cc.four_pi_c_over_mpc * (1.0 + rzp) * (dmpc * dmpc);
     *dnum_out = nden * tres * cosmo_fact;
 }
 

@@ -160,7 +160,7 @@ __device__ __forceinline__ void fold_draw(const RealizeArgs& a, const Ent& e, in
 }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(RZ_THREADS, nacc_of(VARIANT) == 1 ? 3 : 2)
+__global__ void __launch_bounds__(RZ_THREADS, nacc_of(VARIANT) == 1 ? 4 : 2)
 realize_kernel(RealizeArgs a) {
     constexpr int NACC = nacc_of(VARIANT);
     using Ent = CellEntry<NACC>;
@@ -185,7 +185,7 @@ realize_kernel(RealizeArgs a) {
     const bool supplied = a.counts != nullptr;
     const bool vec4 = (nf == FGROUP) && ((a.F & 3) == 0);   // 32 B-aligned frequency groups
 
-    if (tid < RCP_TABLE) s_rcp[tid] = tid > 0 ? 1.0 / (double)tid : 0.0;
+    for (int i = tid; i < RCP_TABLE; i += blockDim.x) s_rcp[i] = i > 0 ? 1.0 / (double)i : 0.0;
 
     double acc[FGROUP][NACC];
     double vmax[FGROUP];

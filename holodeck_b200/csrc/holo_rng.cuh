@@ -11,8 +11,9 @@
 //   lam < 2^-8   TINY  : P(n>=1) = -expm1(-lam) <= 0.4%.  One 32-bit word decides "n = 0" for all
 //                        but a fraction ~lam of the draws (four draws share one Philox block); the
 //                        rest extend the word to 64 bits and invert the survival function.
-//   lam < 10     SMALL : inversion by sequential search on the survival function, 64-bit uniform.
-//   lam >= 10    PTRS  : transformed rejection (Hormann 1993; the algorithm numpy uses, numpy/random/
+//   lam < 32     SMALL : inversion by sequential search on the survival function, 64-bit uniform
+//                        (all lanes of a warp share lam, so the walk lengths are similar: lock-step friendly).
+//   lam >= 32    PTRS  : transformed rejection (Hormann 1993; the algorithm numpy uses, numpy/random/
 //                        src/distributions/distributions.c:random_poisson_ptrs).  The exact
 //                        acceptance test is evaluated without lgamma: Stirling's series for ln k!
 //                        and lam*[x-(1+x)ln(1+x)], x=(k-lam)/lam, for the log-pmf (one log1p + one log).
@@ -114,6 +115,7 @@ HOLO_HD uint64_t prob_to_u64(double p) {   // floor(p * 2^64) for p in [0,1)
 enum { CLS_EMPTY = 0, CLS_TINY = 1, CLS_SMALL = 2, CLS_PTRS = 3, CLS_NORMAL = 4 };
 
 constexpr double TINY_LAM = 0.00390625;   // 2^-8
+constexpr double PTRS_MIN_LAM = 32.0;      // below: inversion from 0 (lock-step friendly), above: PTRS
 
 struct FPrep {
     double lam;
@@ -129,7 +131,7 @@ struct FPrep {
 HOLO_HD int classify_draw(double lam, double thresh) {
     if (!(lam > 0.0)) return CLS_EMPTY;
     if (lam > thresh) return CLS_NORMAL;
-    if (lam >= 10.0) return CLS_PTRS;
+    if (lam >= PTRS_MIN_LAM) return CLS_PTRS;
     return lam < TINY_LAM ? CLS_TINY : CLS_SMALL;
 }
 
@@ -141,7 +143,7 @@ HOLO_HD int prep_draw(double lam, double thresh, FPrep& p) {
         p.a0 = sqrt(lam);
         return CLS_NORMAL;
     }
-    if (lam >= 10.0) {
+    if (lam >= PTRS_MIN_LAM) {
         double b = 0.931 + 2.53 * sqrt(lam);
         p.a0 = b;
         p.a1 = 0.9277 - 3.6224 / (b - 2.0);
@@ -158,7 +160,7 @@ HOLO_HD int prep_draw(double lam, double thresh, FPrep& p) {
 
 // n >= 1 is already known (u < t): find n by walking the survival function.  v = u * 2^-64.
 // `rcp` (optional) is a table of 1/n for n < RCP_TABLE so the walk has no division.
-constexpr int RCP_TABLE = 64;
+constexpr int RCP_TABLE = 96;
 
 HOLO_HD double invert_survival(double lam, double T, double p1, double v, const double* rcp = nullptr) {
     double n = 1.0;

@@ -124,6 +124,7 @@ void emu_dbn_2pwl(holo_cy_consts c, const double* fobs, int F, double sepa_init,
                 te += dt[k];
                 tevo[k + 1] = te;
             }
+            const MqConsts mqc = mq_consts(cc, mt, mr);
             Track2pwl t;
             t.frst = frst.data(); t.tevo = tevo.data(); t.dt = dt.data(); t.nsteps = nsteps;
             t.tage = grid_age; t.gz = grid_z; t.gdc = grid_dcom; t.n_interp = n_interp;
@@ -132,7 +133,7 @@ void emu_dbn_2pwl(holo_cy_consts c, const double* fobs, int F, double sepa_init,
                 for (int ff = 0; ff < F; ++ff) {
                     double rz = -1.0, dn = 0.0;
                     int64_t b = (int64_t)mq * Z + kk;
-                    dbn_2pwl_cell(cc, t, mt, mr, norm, rchar, gi, go, nden[b], gmt_time[b], zage[kk],
+                    dbn_2pwl_cell(cc, mqc, t, norm, rchar, gi, go, nden[b], gmt_time[b], zage[kk],
                                   fobs[ff], &rz, &dn);
                     redz_final[b * F + ff] = rz;
                     diff_num[b * F + ff] = dn;
