@@ -45,3 +45,4 @@ from holodeck_b200 import sams            # noqa: E402,F401
 from holodeck_b200.sams import sam        # noqa: E402,F401
 from holodeck_b200 import dist            # noqa: E402,F401
 from holodeck_b200 import librarian       # noqa: E402,F401
+from holodeck_b200 import extensions      # noqa: E402,F401

@@ -416,7 +416,7 @@ __global__ void rank_inverse_kernel(const int32_t* __restrict__ order, int64_t n
         rank[order[p]] = (int32_t)p;
 }
 
-constexpr int HEAD_ROWS = 1024;   // rank positions per block
+constexpr int HEAD_ROWS = 128;    // rank positions per block = granularity of the head cut K_f
 
 // bsum[blk][f] = sum over rank positions of the block of P(cell occupied) at frequency f
 __global__ void __launch_bounds__(256)

@@ -107,3 +107,27 @@ def test_empty_and_degenerate_inputs():
     lam = np.full((1, 1, 1, 1), 3.0e10)
     gwb = cyutils.sam_poisson_gwb(lam, np.ones_like(lam), 2000, seed=4)
     assert abs(gwb.mean() / 3.0e10 - 1) < 1e-6 and abs(gwb.std() / np.sqrt(3.0e10) - 1) < 0.1 and np.any(gwb != np.floor(gwb))
+
+
+def test_realizer_sam_weights():
+    """extensions.Realizer_SAM: (ncell, R) Poisson weights with the right mean and bin-centre samples."""
+    import holodeck_b200 as holo
+    from holodeck_b200 import host_relations, utils
+    from holodeck_b200.constants import YR
+    sam = holo.sams.Semi_Analytic_Model(shape=(9, 8, 10), mmbulge=host_relations.MMBulge_KH2013(scatter_dex=0.0))
+    _, fobs_edges = utils.pta_freqs(16.03*YR, 4)
+    real = holo.extensions.Realizer_SAM(fobs_edges / 2.0, sam=sam, hard=holo.hardening.Hard_GW())
+    names, samples, weights = real(nreals=300, seed=3)
+    ncell = 8 * 7 * 9 * 4
+    assert names == ['mtot', 'mrat', 'redz', 'fobs'] and all(ss.shape == (ncell,) for ss in samples)
+    assert weights.shape == (ncell, 300) and np.all(weights >= 0) and np.all(weights == np.floor(weights))
+    grid, dnum, redz_final = sam.dynamic_binary_number_at_fobs(holo.hardening.Hard_GW(), utils.midpoints(fobs_edges) / 2.0)
+    number = holo.sams.sam_cyutils.integrate_differential_number_3dx1d([sam.mtot, sam.mrat, sam.redz, fobs_edges / 2.0], dnum).flatten()
+    sel = (number > 0.05) & (number < 1e6)
+    zsc = (weights[sel].mean(axis=1) - number[sel]) / np.sqrt(number[sel] / 300)
+    assert np.all(np.abs(zsc) < 6) and abs(zsc.mean()) < 0.5
+    assert np.all(weights[number == 0] == 0)
+    _, s2, w2 = real(nreals=3, clean=True, seed=3)
+    assert len(w2) == 3 and all(len(ss[0]) == len(ww) for ss, ww in zip(s2, w2))
+    with pytest.raises(ValueError):
+        holo.extensions.Realizer_SAM(fobs_edges / 2.0)
