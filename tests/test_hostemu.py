@@ -144,6 +144,79 @@ def test_emu_samplers_are_exact_poisson(emu):
     assert np.any(dd != np.floor(dd)) and abs(dd.mean() / 5e10 - 1) < 1e-7 and abs(dd.std() / np.sqrt(5e10) - 1) < 0.03
 
 
+def test_emu_table_sampler(emu):
+    """TABLE class of the realization kernel (32-bit CDF thresholds + exact slow path): the thresholds are
+    floor(cdf 2^32) to within one unit, fast and slow path agree draw by draw, and both are exact Poisson."""
+    import scipy.stats as st
+    emu.emu_draw_table.argtypes = [C.c_double, C.c_int64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    emu.emu_draw_table.restype = C.c_int
+    N = 300000
+    for ii, lam in enumerate([2.0**-8, 0.05, 0.7, 3.0, 31.0, 33.0, 86.0, 400.0, 1500.0, 4000.0]):
+        dd = np.zeros(N)
+        tab = np.zeros(1024, dtype=np.uint32)
+        kmin, nslow = C.c_int(0), C.c_int64(0)
+        W = emu.emu_draw_table(lam, N, 77 + ii, 0, P(dd), P(tab), C.byref(kmin), C.byref(nslow))
+        assert 1 <= W <= 1024
+        kk = kmin.value + np.arange(W)
+        cdf = st.poisson.cdf(kk, lam)
+        assert np.all(np.abs(tab[:W].astype(np.float64) - np.minimum(np.floor(cdf * 2.0**32), 2.0**32 - 1)) <= 1.0)
+        assert st.poisson.cdf(kmin.value - 1, lam) < 2.0**-64 and st.poisson.sf(kk[-1], lam) < 1e-9
+        assert nslow.value <= 5 + 50 * N * 3 * W / 2.0**32
+        # every draw through the exact slow path gives the same counts
+        d1 = np.zeros(30000)
+        emu.emu_draw_table(lam, 30000, 77 + ii, 1, P(d1), None, None, None)
+        assert np.array_equal(d1, dd[:30000])
+        assert abs(dd.mean() - lam) < 5.0 * np.sqrt(lam / N)
+        if lam >= 0.5:
+            lo, hi = int(st.poisson.ppf(1e-3, lam)), int(st.poisson.ppf(1 - 1e-3, lam)) + 1
+            nb = min(60, hi - lo + 1)
+            edges = np.unique(np.linspace(lo, hi + 1, nb + 1).astype(np.int64))
+            which = np.searchsorted(edges, dd.astype(np.int64), side="right") - 1
+            inside = (dd >= edges[0]) & (dd < edges[-1])
+            obs = np.bincount(which[inside], minlength=edges.size - 1).astype(float)
+            exp = N * (st.poisson.cdf(edges[1:] - 1, lam) - st.poisson.cdf(edges[:-1] - 1, lam))
+            sel = exp > 20
+            chi2 = np.sum((obs[sel] - exp[sel])**2 / exp[sel])
+            assert st.chi2.sf(chi2, sel.sum()) > 1e-4, (lam, chi2, sel.sum())
+        else:
+            p1 = -np.expm1(-lam)
+            assert abs(np.mean(dd >= 1) - p1) < 5.0 * np.sqrt(p1 / N)
+
+
+def test_emu_superposition_group(emu):
+    """`draw_group` (all elements of a pass with lam < 0.25 drawn as one Poisson process, events assigned to
+    members with probability lam_k / Lambda): member counts are independent Poisson(lam_k)."""
+    import scipy.stats as st
+    emu.emu_draw_group_members.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_void_p]
+    rng = np.random.default_rng(5)
+    N = 200000
+    for K, scale in [(4, 0.25), (64, 0.25), (400, 0.2), (512, 1e-5)]:
+        lam = rng.uniform(0.0, 1.0, K)**3 * scale
+        lam[0] = scale * 0.999
+        out = np.zeros((N, K))
+        emu.emu_draw_group_members(P(lam), K, N, 31 + K, P(out))
+        assert np.all(out == np.floor(out)) and np.all(out >= 0)
+        tot = out.sum(axis=1)
+        Lam = lam.sum()
+        assert abs(tot.mean() - Lam) < 5.0 * np.sqrt(Lam / N)
+        assert abs(tot.var() - Lam) < 6.0 * np.sqrt((Lam + 2 * Lam**2) / N) + 1e-12
+        # member marginals: mean, P(n >= 1), P(n >= 2)
+        big = lam * N > 50
+        if not big.any():
+            continue
+        zz = (out.mean(axis=0)[big] - lam[big]) / np.sqrt(lam[big] / N)
+        assert np.max(np.abs(zz)) < 5.0
+        p1 = -np.expm1(-lam[big])
+        z1 = ((out[:, big] >= 1).mean(axis=0) - p1) / np.sqrt(p1 / N)
+        assert np.max(np.abs(z1)) < 5.0
+        p2 = st.poisson.sf(1, lam[0])
+        assert abs((out[:, 0] >= 2).mean() - p2) < 5.0 * np.sqrt(p2 / N) + 1e-9
+        # independence of the two largest members: covariance ~ 0
+        jj = np.argsort(lam)[-2:]
+        cov = np.mean(out[:, jj[0]] * out[:, jj[1]]) - out[:, jj[0]].mean() * out[:, jj[1]].mean()
+        assert abs(cov) < 5.0 * np.sqrt(lam[jj[0]] * lam[jj[1]] / N) + 1e-12
+
+
 def test_emu_philox_known_answers(emu):
     """Random123 known-answer vectors for Philox4x32-10."""
     emu.emu_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
