@@ -167,9 +167,9 @@ __device__ __forceinline__ void fold_static(const RealizeArgs& a, const Rec& rec
             for (int k = 1; k < 4; ++k) acc[FI][k < NACC ? k : 0] += nc * w3[k - 1];
         }
     } else {
-        if (n < 1.0) return;                                                // pyx:1333, 1490, 1727
+        // `if num < 1: continue` (pyx:1333, 1490, 1727): counts are integers (or > 1e10), so an empty draw adds zero
         if (rec.meta & META_HEAD) {
-            push_event(a, f0 + FI, r, rec.cell, n);
+            if (n >= 1.0) push_event(a, f0 + FI, r, rec.cell, n);
         } else {
             const double nc = n * cur;
             acc[FI][0] += nc;                                               // pyx:1342, 1505, 1745
@@ -237,6 +237,7 @@ realize_kernel(RealizeArgs a) {
     __shared__ double s_totlam;
     __shared__ int s_np;
     __shared__ int s_gspec[3];                          // kmin, W, lg of the group's table
+    __shared__ uint32_t s_words[4][RPT][RZ_THREADS];    // each thread's Philox block of the current cell, per slot
     extern __shared__ uint32_t s_pool[];                // POOL_ENTRIES thresholds
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -445,9 +446,6 @@ realize_kernel(RealizeArgs a) {
         // ---- phase A, lock-step: every thread walks the main records; the (up to four) draws of a cell consume
         //      the words of one Philox block per slot, in record order
         {
-            uint32_t w0[RPT], w1[RPT], w2[RPT], w3[RPT];
-#pragma unroll
-            for (int u = 0; u < RPT; ++u) w0[u] = w1[u] = w2[u] = w3[u] = 0u;
             int ord = 0;
             for (int i = 0; i < nmain; ++i) {
                 const Rec rec = s_rec[i];
@@ -458,7 +456,8 @@ realize_kernel(RealizeArgs a) {
                     for (int u = 0; u < RPT; ++u) {
                         key.real = real_first + (uint32_t)u * blockDim.x;
                         const Philox4 hi = group_bits(key, (uint32_t)rec.cell, (uint32_t)fg, PURPOSE_GROUP_HI);
-                        w0[u] = hi.v[0]; w1[u] = hi.v[1]; w2[u] = hi.v[2]; w3[u] = hi.v[3];
+                        s_words[0][u][tid] = hi.v[0]; s_words[1][u][tid] = hi.v[1];     // (thread-private columns:
+                        s_words[2][u][tid] = hi.v[2]; s_words[3][u][tid] = hi.v[3];     //  no synchronisation needed)
                     }
                     ord = 0;
                 }
@@ -467,10 +466,7 @@ realize_kernel(RealizeArgs a) {
                 if (cls == CLS_TABLE) {
                     uint32_t word[RPT], q[RPT];
 #pragma unroll
-                    for (int u = 0; u < RPT; ++u) {     // next word of the cell's block
-                        word[u] = w0[u];
-                        w0[u] = w1[u]; w1[u] = w2[u]; w2[u] = w3[u];
-                    }
+                    for (int u = 0; u < RPT; ++u) word[u] = s_words[ord][u][tid];     // next word of the cell's block
                     const int W = (int)((meta >> 12) & 4095u), lg = (int)((meta >> 8) & 15u);
                     table_ladder_n<RPT>(s_pool, rec.toff, W, lg, word, q);
 #pragma unroll

@@ -481,15 +481,24 @@ HOLO_HD double draw_table_fast(const uint32_t* t, int kmin, int W, uint32_t hi, 
 // per rung; N independent draws from the same table (the realization slots a thread carries) climb the
 // ladder together, which shares the rung dispatch and gives the scheduler N independent dependency chains.
 // On return q[u] = toff + count (pool index of the first threshold above draw u).
+// (thresholds are addressed by BYTE offset from `pool`, so that a rung is LDS [reg + imm], compare, predicated add)
+HOLO_HD uint32_t pool_at(const uint32_t* pool, uint32_t byte_off) {
+    return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(pool) + byte_off);
+}
+
 template <int N>
 HOLO_HD void table_ladder_n(const uint32_t* pool, uint32_t toff, int W, int lg, const uint32_t (&hi)[N], uint32_t (&q)[N]) {
     const uint32_t P = 1u << lg;
-#define HOLO_RUNG(step)                                             \
-    _Pragma("unroll") for (int u = 0; u < N; ++u) {                 \
-        if (pool[q[u] + ((step) - 1u)] <= hi[u]) q[u] += (step);    \
+    uint32_t qb[N];   // byte offsets
+#define HOLO_RUNG(step)                                                         \
+    _Pragma("unroll") for (int u = 0; u < N; ++u) {                             \
+        if (pool_at(pool, qb[u] + 4u * ((step) - 1u)) <= hi[u]) qb[u] += 4u * (step); \
     }
+    {
+        const uint32_t top = pool_at(pool, 4u * (toff + P - 1u)), skip = 4u * ((uint32_t)W - P);
 #pragma unroll
-    for (int u = 0; u < N; ++u) q[u] = toff + ((pool[toff + P - 1u] <= hi[u]) ? (uint32_t)W - P : 0u);
+        for (int u = 0; u < N; ++u) qb[u] = 4u * toff + ((top <= hi[u]) ? skip : 0u);
+    }
     switch (lg) {
         case 10: HOLO_RUNG(512u)   // fall through
         case 9: HOLO_RUNG(256u)
@@ -505,13 +514,15 @@ HOLO_HD void table_ladder_n(const uint32_t* pool, uint32_t toff, int W, int lg, 
     }
     HOLO_RUNG(1u)
 #undef HOLO_RUNG
+#pragma unroll
+    for (int u = 0; u < N; ++u) q[u] = qb[u] >> 2;
 }
 
 // Is the draw whose ladder ended at pool index q decided by its 32-bit word?  pool[toff - 1] = 0 and
 // pool[toff + W] = 2^32 - 1 are sentinels, so the two neighbouring thresholds can be read blindly.
 HOLO_HD bool table_ambiguous(const uint32_t* pool, uint32_t toff, int W, uint32_t q, uint32_t hi) {
-    const uint32_t below = hi - pool[q - 1u], above = pool[q] - hi;
-    return ((int)(q - toff) >= W) | (below <= 1u) | (above <= 1u);
+    const uint32_t below = hi - pool_at(pool, 4u * q - 4u), above = pool_at(pool, 4u * q) - hi;
+    return (q >= toff + (uint32_t)W) | (below <= 1u) | (above <= 1u);
 }
 
 // single TABLE draw: the count, or -1 when the 32-bit word does not decide it (toff >= 1)
