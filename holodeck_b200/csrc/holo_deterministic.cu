@@ -227,13 +227,32 @@ dbn_2pwl_kernel(CyConsts cc, const double* __restrict__ fobs, int F, double sepa
     const MqConsts mqc = mq_consts(cc, mt, mr);
     int64_t base = (int64_t)mq * Z;
     int nzf = Z * F;
+    // phase 2: one thread per redshift finds, for every target frequency, the first step whose right edge reaches
+    // it -- bisection for the lowest frequency, then a merge walk (both sequences ascend); when `fobs` is not
+    // ascending every frequency is bisected on its own.
+    unsigned short* s_lo = reinterpret_cast<unsigned short*>(s_fobs + F);   // (Z, F)
+    for (int kk = tid; kk < Z; kk += DBN_THREADS) {
+        const double gmt = gmt_time[base + kk], az = s_zage[kk];
+        int lo = 0;
+        double fprev = 0.0;
+        for (int ff = 0; ff < F; ++ff) {
+            const double ft = s_fobs[ff];
+            if (ff == 0 || ft < fprev) lo = dbn_2pwl_first_step(t, gmt, az, ft);
+            else lo = dbn_2pwl_next_step(t, gmt, az, ft, lo);
+            fprev = ft;
+            s_lo[kk * F + ff] = (unsigned short)lo;
+        }
+    }
+    __syncthreads();
+    // phase 3: every (z,f) pair evaluates its (one or two) candidate steps; f is the fastest index, so the
+    // two stores of a warp are fully coalesced
     for (int idx = tid; idx < nzf; idx += DBN_THREADS) {
         int kk = idx / F, ff = idx - kk * F;
         double rz = -1.0, dn = 0.0;                                      // pyx:460-461
         double gmt = gmt_time[base + kk];
         double nd = nden[base + kk];
-        dbn_2pwl_cell(cc, mqc, t, norm, rchar, gamma_inner, gamma_outer, nd, gmt, s_zage[kk],
-                      s_fobs[ff], &rz, &dn);
+        dbn_2pwl_cell_from(cc, mqc, t, norm, rchar, gamma_inner, gamma_outer, nd, gmt, s_zage[kk],
+                           s_fobs[ff], (int)s_lo[idx], &rz, &dn);
         int64_t o = (base + kk) * F + ff;
         redz_final[o] = rz;
         diff_num[o] = dn;
@@ -445,7 +464,9 @@ int holo_dbn_2pwl(holo_cy_consts cc, const double* fobs_orb, int F, double sepa_
     HOLO_REQUIRE(fobs_orb && hard_norm && nden && mtot && mrat && redz && gmt_time && grid_z &&
                  grid_dcom && grid_age && redz_final && diff_num, "holo_dbn_2pwl: NULL argument");
     HOLO_REQUIRE(M > 0 && Q > 0 && Z > 0 && F > 0 && num_steps > 0 && n_interp >= 2, "holo_dbn_2pwl: bad shape");
-    size_t smem = ((size_t)5 * (num_steps + 1) + 3 * (size_t)n_interp + Z + F) * sizeof(double);
+    HOLO_REQUIRE(num_steps < 65535, "holo_dbn_2pwl: num_steps must fit 16 bits");
+    size_t smem = ((size_t)5 * (num_steps + 1) + 3 * (size_t)n_interp + Z + F) * sizeof(double) +
+                  (size_t)Z * F * sizeof(unsigned short);
     HOLO_REQUIRE(smem <= 200 * 1024, "holo_dbn_2pwl: num_steps / table too large for shared memory");
     if (smem > 48 * 1024)
         HOLO_CUDA(cudaFuncSetAttribute(dbn_2pwl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -237,18 +237,29 @@ HOLO_HD double fobs_right_of_step(const Track2pwl& t, int s, double gmt, double 
     return t.frst[s + 1] / (1.0 + redz_right);
 }
 
-// Returns true (and fills redz/dnum) iff some integration step brackets `ftarget`; when several do
-// (exact ties at step boundaries) the LAST one wins, as in the reference's step-major loop order.
-HOLO_HD bool dbn_2pwl_cell(const CyConsts& cc, const MqConsts& mq, const Track2pwl& t, double norm,
-                           double rchar, double gamma_inner, double gamma_outer, double nden,
-                           double gmt, double age_z, double ftarget, double* redz_out,
-                           double* dnum_out) {
-    // first step whose right edge reaches the target (fobs_right is non-decreasing in s)
+// First step whose right edge reaches `ftarget` (fobs_right is non-decreasing in s): bisection.
+HOLO_HD int dbn_2pwl_first_step(const Track2pwl& t, double gmt, double age_z, double ftarget) {
     int lo = 0, hi = t.nsteps;
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
         if (fobs_right_of_step(t, mid, gmt, age_z) >= ftarget) hi = mid; else lo = mid + 1;
     }
+    return lo;
+}
+
+// The same quantity for the next (higher) target frequency, walking up from the previous answer.
+HOLO_HD int dbn_2pwl_next_step(const Track2pwl& t, double gmt, double age_z, double ftarget, int lo) {
+    while (lo < t.nsteps && fobs_right_of_step(t, lo, gmt, age_z) < ftarget) ++lo;
+    return lo;
+}
+
+// Given `lo` = first step whose right edge reaches the target: returns true (and fills redz/dnum) iff some
+// integration step brackets `ftarget`; when several do (exact ties at step boundaries) the LAST one wins,
+// as in the reference's step-major loop order.
+HOLO_HD bool dbn_2pwl_cell_from(const CyConsts& cc, const MqConsts& mq, const Track2pwl& t, double norm,
+                                double rchar, double gamma_inner, double gamma_outer, double nden,
+                                double gmt, double age_z, double ftarget, int lo, double* redz_out,
+                                double* dnum_out) {
     bool found = false;
     for (int s = lo; s < t.nsteps; ++s) {
         double time_right = t.tevo[s + 1] + gmt + age_z;               // pyx:659
@@ -280,6 +291,15 @@ HOLO_HD bool dbn_2pwl_cell(const CyConsts& cc, const MqConsts& mq, const Track2p
         found = true;
     }
     return found;
+}
+
+HOLO_HD bool dbn_2pwl_cell(const CyConsts& cc, const MqConsts& mq, const Track2pwl& t, double norm,
+                           double rchar, double gamma_inner, double gamma_outer, double nden,
+                           double gmt, double age_z, double ftarget, double* redz_out,
+                           double* dnum_out) {
+    const int lo = dbn_2pwl_first_step(t, gmt, age_z, ftarget);
+    return dbn_2pwl_cell_from(cc, mq, t, norm, rchar, gamma_inner, gamma_outer, nden, gmt, age_z, ftarget, lo,
+                              redz_out, dnum_out);
 }
 
 // =================================================================================================
