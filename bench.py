@@ -328,14 +328,27 @@ def run_b200(args):
     }
     dom = max((kk for kk in stages if kk in alg_bytes), key=lambda kk: stages[kk])
     ach = alg_bytes[dom] / (stages[dom] * 1e-3) / 1e9
+    # per-launch DRAM traffic / instruction counts of the same kernels from the committed `ncu --set full` captures
+    ncu = {}
+    try:
+        ncu = json.loads((ROOT / "profiles" / "ncu_metrics.json").read_text())
+    except Exception:
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                "ms": stages[dom], "algorithmic_bytes": alg_bytes[dom]}
+                "frac": ach / pk["hbm_gbs"], "traffic": ncu.get(dom, {}).get("dram_bytes_per_launch"),
+                "peak_source": pk["source"], "ms": stages[dom], "algorithmic_bytes": alg_bytes[dom],
+                "note": ("the dominant kernel draws R Poisson counts per grid element out of shared memory: it is bound by "
+                         "instruction issue, not HBM (see kernels.loudest_draw); `traffic` is per launch from "
+                         "profiles/ncu_metrics.json")}
     per_kernel = {}
     for kk, bb in alg_bytes.items():
         if kk in stages and stages[kk] > 0:
             gbs = bb / (stages[kk] * 1e-3) / 1e9
             per_kernel[kk] = {"ms": round(stages[kk], 4), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / pk["hbm_gbs"], 4)}
+            if kk in ncu:
+                per_kernel[kk]["ncu"] = {"dram_bytes_per_launch": ncu[kk]["dram_bytes_per_launch"],
+                                         "warp_inst_per_launch": ncu[kk]["warp_inst_per_launch"],
+                                         "issue_active_pct": ncu[kk]["issue_active_pct"], "source": ncu[kk]["source"]}
     # the draw kernel is instruction-issue bound, not HBM bound: nominal 25 thread-instructions per
     # cell-realization against 148 SM x 4 schedulers x 32 lanes x clock
     clk = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
@@ -343,6 +356,12 @@ def run_b200(args):
     if "loudest_draw" in stages:
         rate = ncell * R / (stages["loudest_draw"] * 1e-3)
         per_kernel["loudest_draw"].update({"cell_real_per_s": rate, "issue_frac_nominal25": round(rate * 25 / issue_peak, 4)})
+        if "loudest_draw" in ncu:
+            # measured: warp instructions of one launch (ncu) / live duration, against 148 SM x 4 issue slots x clock
+            wi = ncu["loudest_draw"]["warp_inst_per_launch"]
+            per_kernel["loudest_draw"]["issue_frac_measured"] = round(
+                wi / (stages["loudest_draw"] * 1e-3) / (148 * 4 * clk * 1e6), 4)
+            per_kernel["loudest_draw"]["thread_inst_per_cell_realization"] = round(wi * 32 / (ncell * R), 2)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

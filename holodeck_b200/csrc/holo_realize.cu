@@ -47,6 +47,7 @@ __host__ __device__ constexpr bool has_events(int v) {
 __host__ __device__ constexpr bool has_max(int v) { return v == V_SSBG || v == V_SSBG_PAR; }
 
 constexpr int RZ_THREADS = 256;      // threads per CTA (max); each thread carries rpt_of(VARIANT) realizations
+constexpr int NSCAN = 256;           // cells scanned per pass (max) = threads per CTA
 constexpr int FGROUP = 4;            // frequencies per CTA (4 doubles = one 32 B sector per cell)
 constexpr int POOL_ENTRIES = 6144;   // 32-bit CDF thresholds per pass (24 KB of dynamic shared memory)
 constexpr int GROUP_RESERVE = 288;   // head of the pool: CDF table of the pass's superposition group
@@ -220,66 +221,28 @@ static __device__ __noinline__ void build_table_warp(double lam, uint32_t* t, in
     }
 }
 
+// Stage the next run of cells of a pass (see the kernel): thread <-> cell, elements compacted in (cell, frequency)
+// order into `s_rec` (main records from 0 up, group members from NREC-1 down).  Returns the number of cells
+// consumed; *s_tot / *s_totlam receive the packed record counts and the group's total expectation value.
+// The CTA always has NSCAN threads (idle in the draw loops when R is small), so the pass boundaries -- and with
+// them the membership of the superposition groups -- never depend on how the realizations are tiled.
 template <int VARIANT>
-__global__ void __launch_bounds__(RZ_THREADS, min_ctas_of(VARIANT))
-realize_kernel(RealizeArgs a) {
+static __device__ __forceinline__ int stage_pass(const RealizeArgs& a, int64_t cb, int64_t c_hi, int f0, int nf, Rec* s_rec,
+                                              double* s_w3, double* s_w4, double* s_gcum, unsigned long long* s_wsum,
+                                              double* s_wlam, unsigned long long* s_tot, double* s_totlam) {
     constexpr int NACC = nacc_of(VARIANT);
-    constexpr int RPT = rpt_of(VARIANT);
     constexpr int NREC = nrec_of(NACC);
-    __shared__ __align__(16) Rec s_rec[NREC];           // main records grow from 0, group records from NREC-1 down
-    __shared__ double s_w3[NACC > 1 ? NREC : 1][3];     // mt, mr, rz of the record's cell (parameter variants)
-    __shared__ double s_w4[NACC > 4 ? NREC : 1][4];     // redz_final, dcom, sepa, angs of the element
-    __shared__ double s_gcum[NREC];                     // inclusive cumulative expectation of the group members
-    __shared__ unsigned short s_plist[NREC];            // main records of class PTRS
-    __shared__ unsigned long long s_wsum[RZ_THREADS / 32];
-    __shared__ double s_wlam[RZ_THREADS / 32];
-    __shared__ unsigned long long s_tot;
-    __shared__ double s_totlam;
-    __shared__ int s_np;
-    __shared__ int s_gspec[3];                          // kmin, W, lg of the group's table
-    __shared__ uint32_t s_words[4][RPT][RZ_THREADS];    // each thread's Philox block of the current cell, per slot
-    extern __shared__ uint32_t s_pool[];                // POOL_ENTRIES thresholds
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarp = blockDim.x >> 5;
-    const int chunk_id = blockIdx.x;
-    const int fg = blockIdx.y;
-    const int f0 = fg * FGROUP;
-    const int r_first = blockIdx.z * (blockDim.x * RPT) + tid;      // local realization of slot t = 0
-    const int64_t c_lo = (int64_t)chunk_id * a.chunk;
-    int64_t c_hi = c_lo + a.chunk;
-    if (c_hi > a.ncell) c_hi = a.ncell;
-    const int nf = (a.F - f0) < FGROUP ? (a.F - f0) : FGROUP;
+    constexpr int nwarp = NSCAN / 32;
     const bool supplied = a.counts != nullptr;
     const bool vec4 = (nf == FGROUP) && ((a.F & 3) == 0);   // 32 B-aligned frequency groups
-
-    double acc[RPT][FGROUP][NACC];
-    double vmax[RPT][FGROUP];
-    int imax[RPT][FGROUP];
-#pragma unroll
-    for (int t = 0; t < RPT; ++t) {
-#pragma unroll
-        for (int fi = 0; fi < FGROUP; ++fi) {
-#pragma unroll
-            for (int k = 0; k < NACC; ++k) acc[t][fi][k] = 0.0;
-            vmax[t][fi] = 0.0;
-            imax[t][fi] = -1;
-        }
-    }
-
-    DrawKey key;
-    key.k0 = a.k0; key.k1 = a.k1;
-    key.real = 0;
-    key.stream = has_events(VARIANT) ? STREAM_LOUD : (has_max(VARIANT) ? STREAM_SSBG : STREAM_GWB);
-    const uint32_t real_first = (uint32_t)(a.r0 + r_first);
-
-    int64_t cb = c_lo;
-    while (cb < c_hi) {
-        // ---- stage the next run of cells: thread <-> cell, elements compacted in (cell, frequency) order.  The run
-        //      ends where the record buffer (NREC elements) or the table pool is full.
-        __syncthreads();   // previous pass fully consumed
-        const int64_t c = cb + tid;
-        const bool inrange = c < c_hi;
+    __syncthreads();   // previous pass fully consumed
+    int ncons = 0;
+    unsigned long long carry = 0;
+    double carry_lam = 0.0;
+    for (int sbase = 0; sbase < NSCAN; sbase += NSCAN) {      // (a single round: blockDim.x == NSCAN)
+        const int64_t c = cb + sbase + tid;
+        const bool inrange = (c < c_hi) && (sbase + tid < NSCAN);
         unsigned clsw = 0;            // CLS_* byte per frequency slot
         unsigned nmain_t = 0, ngrp_t = 0, need_t = 0;
         double glam_t = 0.0;
@@ -310,7 +273,7 @@ realize_kernel(RealizeArgs a) {
                 clsw |= (unsigned)cls << (8 * fi);
             }
         }
-        // block-wide inclusive scans in cell order: (main | group << 11 | pool entries << 22) and the group's lambda
+        // block-wide inclusive scans in cell order: (main | group << 11 | pool entries << 22), group's lambda
         unsigned long long incl = (unsigned long long)nmain_t | ((unsigned long long)ngrp_t << 11) |
                                   ((unsigned long long)need_t << 22);
         double glam = glam_t;
@@ -322,19 +285,25 @@ realize_kernel(RealizeArgs a) {
         }
         if (lane == 31) { s_wsum[warp] = incl; s_wlam[warp] = glam; }
         __syncthreads();
+        unsigned long long round_tot = carry;
+        double round_lam = carry_lam;
         {
-            unsigned long long pre = 0;
-            double prel = 0.0;
-            for (int w = 0; w < warp; ++w) { pre += s_wsum[w]; prel += s_wlam[w]; }
-            incl += pre;
-            glam = prel + glam;
+            unsigned long long pre = carry;
+            double prel = carry_lam;
+            for (int w = 0; w < nwarp; ++w) {
+                if (w == warp) { incl += pre; glam = prel + glam; }
+                pre += s_wsum[w];
+                prel += s_wlam[w];
+            }
+            round_tot = pre;
+            round_lam = prel;
         }
         const int main_incl = (int)(incl & 2047u), grp_incl = (int)((incl >> 11) & 2047u);
         const int need_incl = (int)(incl >> 22);
         const bool taken = inrange && (main_incl + grp_incl <= NREC) &&
                            (need_incl <= POOL_ENTRIES - GROUP_RESERVE);        // a prefix of the run
-        const int ncons = __syncthreads_count(taken);
-        if (tid == ncons - 1) { s_tot = incl; s_totlam = glam; }
+        const int ntaken = __syncthreads_count(taken);
+        if (ntaken > 0 && tid == ntaken - 1) { *s_tot = incl; *s_totlam = glam; }
         if (taken && clsw != 0) {
             int mi = main_incl - (int)nmain_t;                   // next main record
             int gi = grp_incl - (int)ngrp_t;                     // next group member
@@ -379,20 +348,87 @@ realize_kernel(RealizeArgs a) {
                 s_rec[slot] = rec;
                 if (NACC > 4) {
                     const int64_t o = c * a.F + f0 + fi;
-                    s_w4[slot][0] = a.redz_final[o];
-                    s_w4[slot][1] = a.dcom_final[o];
-                    s_w4[slot][2] = a.sepa[o];
-                    s_w4[slot][3] = a.angs[o];
+                    s_w4[slot * 4 + 0] = a.redz_final[o];
+                    s_w4[slot * 4 + 1] = a.dcom_final[o];
+                    s_w4[slot * 4 + 2] = a.sepa[o];
+                    s_w4[slot * 4 + 3] = a.angs[o];
                 }
                 if (NACC > 1) {
                     const int zz = (int)(c % a.Zb);
                     const int64_t mq = c / a.Zb;
-                    s_w3[slot][0] = a.mt[(int)(mq / a.Qb)];
-                    s_w3[slot][1] = a.mr[(int)(mq % a.Qb)];
-                    s_w3[slot][2] = a.rz[zz];
+                    s_w3[slot * 3 + 0] = a.mt[(int)(mq / a.Qb)];
+                    s_w3[slot * 3 + 1] = a.mr[(int)(mq % a.Qb)];
+                    s_w3[slot * 3 + 2] = a.rz[zz];
                 }
             }
         }
+        ncons += ntaken;
+        carry = round_tot;
+        carry_lam = round_lam;
+        if (ntaken < NSCAN) break;
+    }
+    return ncons;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(RZ_THREADS, min_ctas_of(VARIANT))
+realize_kernel(RealizeArgs a) {
+    constexpr int NACC = nacc_of(VARIANT);
+    constexpr int RPT = rpt_of(VARIANT);
+    constexpr int NREC = nrec_of(NACC);
+    __shared__ __align__(16) Rec s_rec[NREC];           // main records grow from 0, group records from NREC-1 down
+    __shared__ double s_w3[NACC > 1 ? NREC : 1][3];     // mt, mr, rz of the record's cell (parameter variants)
+    __shared__ double s_w4[NACC > 4 ? NREC : 1][4];     // redz_final, dcom, sepa, angs of the element
+    __shared__ double s_gcum[NREC];                     // inclusive cumulative expectation of the group members
+    __shared__ unsigned short s_plist[NREC];            // main records of class PTRS
+    __shared__ unsigned long long s_wsum[RZ_THREADS / 32];
+    __shared__ double s_wlam[RZ_THREADS / 32];
+    __shared__ unsigned long long s_tot;
+    __shared__ double s_totlam;
+    __shared__ int s_np;
+    __shared__ int s_gspec[3];                          // kmin, W, lg of the group's table
+    __shared__ uint32_t s_words[4][RPT][RZ_THREADS];    // each thread's Philox block of the current cell, per slot
+    extern __shared__ uint32_t s_pool[];                // POOL_ENTRIES thresholds
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarp = blockDim.x >> 5;
+    const int fg = blockIdx.x;          // fastest: the CTAs sharing a chunk's 320 B rows run together (L2 reuse)
+    const int chunk_id = blockIdx.y;
+    const int f0 = fg * FGROUP;
+    const int r_first = blockIdx.z * (blockDim.x * RPT) + tid;      // local realization of slot t = 0
+    const int64_t c_lo = (int64_t)chunk_id * a.chunk;
+    int64_t c_hi = c_lo + a.chunk;
+    if (c_hi > a.ncell) c_hi = a.ncell;
+    const int nf = (a.F - f0) < FGROUP ? (a.F - f0) : FGROUP;
+    const bool supplied = a.counts != nullptr;
+    const bool vec4 = (nf == FGROUP) && ((a.F & 3) == 0);   // 32 B-aligned frequency groups
+
+    double acc[RPT][FGROUP][NACC];
+    double vmax[RPT][FGROUP];
+    int imax[RPT][FGROUP];
+#pragma unroll
+    for (int t = 0; t < RPT; ++t) {
+#pragma unroll
+        for (int fi = 0; fi < FGROUP; ++fi) {
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[t][fi][k] = 0.0;
+            vmax[t][fi] = 0.0;
+            imax[t][fi] = -1;
+        }
+    }
+
+    DrawKey key;
+    key.k0 = a.k0; key.k1 = a.k1;
+    key.real = 0;
+    key.stream = has_events(VARIANT) ? STREAM_LOUD : (has_max(VARIANT) ? STREAM_SSBG : STREAM_GWB);
+    const uint32_t real_first = (uint32_t)(a.r0 + r_first);
+
+    int64_t cb = c_lo;
+    while (cb < c_hi) {
+        // ---- stage the next run of cells: thread <-> cell, elements compacted in (cell, frequency) order.  The run
+        //      ends where the record buffer (NREC elements) or the table pool is full.
+        const int ncons = stage_pass<VARIANT>(a, cb, c_hi, f0, nf, s_rec, &s_w3[0][0], &s_w4[0][0], s_gcum, s_wsum, s_wlam, &s_tot,
+                                              &s_totlam);
         const uint32_t pass_id = (uint32_t)cb;        // first cell of the run: names the pass in the Philox counter
         cb += ncons;
         __syncthreads();
@@ -815,28 +851,51 @@ struct FinalArgs {
     int nchunk, Qb, Zb, F, R;
 };
 
+constexpr int FIN_R = 32;      // realizations per block (one 256 B row of `partial` per load)
+constexpr int FIN_SEG = 8;     // chunk segments summed concurrently, then combined in segment order
+
 template <int VARIANT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FIN_R * FIN_SEG)
 final_kernel(FinalArgs a) {
     constexpr int NACC = nacc_of(VARIANT);
-    int64_t fr = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (fr >= (int64_t)a.F * a.R) return;
-    int f = (int)(fr / a.R), r = (int)(fr % a.R);
+    __shared__ double s_sum[FIN_SEG][NACC][FIN_R];
+    __shared__ double s_max[FIN_SEG][FIN_R];
+    __shared__ int s_idx[FIN_SEG][FIN_R];
+    const int rl = threadIdx.x % FIN_R, seg = threadIdx.x / FIN_R;
+    const int f = blockIdx.y;
+    const int r = blockIdx.x * FIN_R + rl;
+    const bool live = r < a.R;
+    const int per = (a.nchunk + FIN_SEG - 1) / FIN_SEG;
+    const int ch0 = seg * per, ch1 = min(a.nchunk, ch0 + per);
     double s[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) s[k] = 0.0;
     double vmax = 0.0;
     int imax = -1;
-    for (int ch = 0; ch < a.nchunk; ++ch) {
-        int64_t pb = ((int64_t)ch * a.F + f) * NACC;
+    if (live) {
+        for (int ch = ch0; ch < ch1; ++ch) {
+            int64_t pb = ((int64_t)ch * a.F + f) * NACC;
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) s[k] += a.partial[(pb + k) * a.R + r];
-        if (has_max(VARIANT)) {
-            int64_t mb = ((int64_t)ch * a.F + f) * a.R + r;
-            double v = a.pmax[mb];
-            if (v > vmax) { vmax = v; imax = a.pidx[mb]; }
+            for (int k = 0; k < NACC; ++k) s[k] += a.partial[(pb + k) * a.R + r];
+            if (has_max(VARIANT)) {
+                int64_t mb = ((int64_t)ch * a.F + f) * a.R + r;
+                double v = a.pmax[mb];
+                if (v > vmax) { vmax = v; imax = a.pidx[mb]; }
+            }
         }
     }
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) s_sum[seg][k][rl] = s[k];
+    s_max[seg][rl] = vmax;
+    s_idx[seg][rl] = imax;
+    __syncthreads();
+    if (seg != 0 || !live) return;
+    for (int g = 1; g < FIN_SEG; ++g) {          // fixed order: chunks ascending
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) s[k] += s_sum[g][k][rl];
+        if (has_max(VARIANT) && s_max[g][rl] > vmax) { vmax = s_max[g][rl]; imax = s_idx[g][rl]; }
+    }
+    const int64_t fr = (int64_t)f * a.R + r;
     if (a.rem) {
 #pragma unroll
         for (int k = 0; k < NACC; ++k) s[k] += a.rem[((int64_t)f * NACC + k) * a.R + r];
@@ -905,8 +964,7 @@ struct Plan {
 static Plan make_plan(int64_t ncell, int F, int R, int variant) {
     Plan p;
     const int nacc = nacc_of(variant), rpt = rpt_of(variant);
-    p.threads = R >= RZ_THREADS ? RZ_THREADS : ((R + 31) / 32) * 32;
-    if (p.threads < 32) p.threads = 32;
+    p.threads = RZ_THREADS;   // always: the staging scan is one thread per cell of a 256-cell window (see stage_pass)
     p.ntiles = (R + p.threads * rpt - 1) / (p.threads * rpt);
     p.nfg = (F + FGROUP - 1) / FGROUP;
     // The cell chunking must not depend on R (or on the realization tiling): per-chunk partial sums are
@@ -976,7 +1034,7 @@ static Layout carve(void* ws, int variant, int64_t ncell, int F, int R, int cap,
 
 template <int VARIANT>
 static int launch_realize(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
-    dim3 grid(p.nchunk, p.nfg, p.ntiles);
+    dim3 grid(p.nfg, p.nchunk, p.ntiles);
     const size_t pool_bytes = sizeof(uint32_t) * POOL_ENTRIES;
     static bool attr_set = false;   // static + dynamic shared memory may exceed the 48 KB default
     if (!attr_set) {
@@ -1033,7 +1091,7 @@ int holo_sam_poisson_gwb(const double* number, const double* h2fdf, int64_t ncel
     FinalArgs fa{};
     fa.partial = l.partial; fa.out0 = gwb; fa.nchunk = p.nchunk; fa.Qb = 1; fa.Zb = 1; fa.F = F; fa.R = R;
     int64_t nfr = (int64_t)F * R;
-    final_kernel<V_GWB><<<(int)((nfr + 255) / 256), 256, 0, st>>>(fa); holo::count_launches(1);
+    final_kernel<V_GWB><<<dim3((R + FIN_R - 1) / FIN_R, F), FIN_R * FIN_SEG, 0, st>>>(fa); holo::count_launches(1);
     timer.mark();
     timer.finish();
     return holo_check_launch("holo_sam_poisson_gwb");
@@ -1127,10 +1185,10 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     FinalArgs fa{};
     fa.partial = l.partial; fa.rem = l.rem; fa.out0 = g->hc2bg; fa.bgpar = g->bgpar;
     fa.nchunk = p.nchunk; fa.Qb = g->Qb; fa.Zb = g->Zb; fa.F = F; fa.R = R;
-    int fblocks = (int)((nfr + 255) / 256);
-    if (v == V_LOUD_PLAIN) final_kernel<V_LOUD_PLAIN><<<fblocks, 256, 0, st>>>(fa);
-    else if (v == V_LOUD_PAR) final_kernel<V_LOUD_PAR><<<fblocks, 256, 0, st>>>(fa);
-    else final_kernel<V_LOUD_PAR_REDZ><<<fblocks, 256, 0, st>>>(fa);
+    const dim3 fblocks((R + FIN_R - 1) / FIN_R, F);
+    if (v == V_LOUD_PLAIN) final_kernel<V_LOUD_PLAIN><<<fblocks, FIN_R * FIN_SEG, 0, st>>>(fa);
+    else if (v == V_LOUD_PAR) final_kernel<V_LOUD_PAR><<<fblocks, FIN_R * FIN_SEG, 0, st>>>(fa);
+    else final_kernel<V_LOUD_PAR_REDZ><<<fblocks, FIN_R * FIN_SEG, 0, st>>>(fa);
     holo::count_launches(1);
     rc = holo_check_launch("holo_loudest: final");
     if (rc) return rc;
@@ -1179,9 +1237,9 @@ int holo_ss_bg_hc(const double* number, const double* h2fdf, int Mb, int Qb, int
     fa.sspar = sspar; fa.ssidx = ssidx; fa.flags = l.flags;
     fa.nchunk = p.nchunk; fa.Qb = Qb; fa.Zb = Zb; fa.F = F; fa.R = R;
     int64_t nfr = (int64_t)F * R;
-    int fblocks = (int)((nfr + 255) / 256);
-    if (par) final_kernel<V_SSBG_PAR><<<fblocks, 256, 0, st>>>(fa);
-    else final_kernel<V_SSBG><<<fblocks, 256, 0, st>>>(fa);
+    const dim3 fblocks((R + FIN_R - 1) / FIN_R, F);
+    if (par) final_kernel<V_SSBG_PAR><<<fblocks, FIN_R * FIN_SEG, 0, st>>>(fa);
+    else final_kernel<V_SSBG><<<fblocks, FIN_R * FIN_SEG, 0, st>>>(fa);
     holo::count_launches(1);
     rc = holo_check_launch("holo_ss_bg_hc");
     if (rc) return rc;

@@ -3,6 +3,8 @@
 
   python profiles/summarize.py launches gpurun_out/launches_r1.csv   > profiles/r1_launches.txt
   python profiles/summarize.py kernel   gpurun_out/realize_r3.ncu-rep > profiles/r1_realize_v3.txt
+  python profiles/summarize.py metrics  gpurun_out/a.ncu-rep [b.ncu-rep ...] > profiles/ncu_metrics.json
+        (per-kernel DRAM bytes / instruction counts per launch that bench.py quotes as `roofline.traffic`)
 """
 import collections
 import csv
@@ -63,5 +65,41 @@ def kernel(path):
                 print(f"{hh:85s} {vv:>22s} {uu}")
 
 
+def metrics(paths):
+    import json
+    short = {"realize_kernel": "loudest_draw", "dbn_2pwl_kernel": "dbn_2pwl", "bin_kernel": "integrate_strain",
+             "norm_2pwl_kernel": "norm_2pwl", "density_kernel": "density"}
+    res = {}
+    for path in paths:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        head = rows[0]
+
+        def val(rr, key):
+            return float(rr[head.index(key)].replace(",", "")) if key in head else None
+        for rr in rows[2:]:
+            name = rr[head.index("Kernel Name")]
+            key = next((vv for kk, vv in short.items() if kk in name), None)
+            if key is None:
+                continue
+            units = rows[1]
+
+            def to_bytes(metric):
+                vv, uu = val(rr, metric), units[head.index(metric)]
+                return vv * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[uu]
+            res[key] = {
+                "kernel": name.split("(")[0], "source": path.replace("gpurun_out/", ""),
+                "dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
+                "warp_inst_per_launch": val(rr, "smsp__inst_executed.sum"),
+                "issue_active_pct": val(rr, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "ms_under_ncu": val(rr, "gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(
+                    units[head.index("gpu__time_duration.sum")], 1.0),
+            }
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "metrics":
+        metrics(sys.argv[2:])
+    else:
+        {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])

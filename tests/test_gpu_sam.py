@@ -218,3 +218,50 @@ def test_realised_moments_all_sampler_classes(holo):
     z2 = (tot.mean(axis=1) - mean_exp) / np.sqrt(var_exp / R)
     assert np.all(np.abs(z2) < 5.0), z2
     assert np.all(ss[..., :-1] >= ss[..., 1:]) or True   # slots follow the rank order of frequency 0 only
+
+
+def test_full_size_named_config_properties(holo):
+    """BASELINE configs[1]/[2] at full size (91x81x101 edges, 40 frequencies), through size-independent properties:
+    sentinel pattern of redz_final, conservation of the integrated number, mean of the realised total against the
+    expectation value, slot ordering at f0, and independence of the realization partition."""
+    import torch
+    import argparse
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import bench
+    from holodeck_b200 import utils, gravwaves, cosmo
+    from holodeck_b200.constants import YR
+    from holodeck_b200.sams import sam_cyutils
+    args = argparse.Namespace(shape=[91, 81, 101], nfreqs=40, realize=256, loudest=10)
+    fobs_cents, fobs_edges = utils.pta_freqs(16.03*YR, 40)
+    sam, hard = bench.make_models(args)
+    redz_final, diff_num = sam_cyutils.dynamic_binary_number_at_fobs(fobs_cents / 2.0, sam, hard, cosmo, device=True)
+    assert redz_final.shape == (91, 81, 101, 40)
+    unreached = redz_final == -1.0
+    assert bool(torch.all(diff_num[unreached] == 0.0)) and bool(torch.all(redz_final[~unreached] >= 0.0))
+    assert bool(torch.all(diff_num >= 0.0))
+    edges = [sam.mtot, sam.mrat, sam.redz, fobs_edges / 2.0]
+    strain = gravwaves._char_strain_sq(edges, redz_final, params=False, dnum=diff_num)
+    number, h2fdf = strain["number"], strain["h2fdf"]
+    assert number.shape == (90, 80, 100, 40)
+    # trapezoid weights sum to the box volume: integrating dnum == 1 gives prod(edge spans) per frequency
+    ones = torch.ones_like(diff_num)
+    vol = sam_cyutils.integrate_differential_number_3dx1d(edges, ones).sum(dim=(0, 1, 2)).cpu().numpy()
+    span = (np.log10(sam.mtot[-1] / sam.mtot[0]) * (sam.mrat[-1] - sam.mrat[0]) * (sam.redz[-1] - sam.redz[0]))
+    assert np.allclose(vol, span * np.diff(np.log(fobs_edges / 2.0)), rtol=1e-12)
+    # realised total (loudest slots + background) against the expectation value, R = 256, L = 10
+    R, L = 256, 10
+    hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=77)
+    assert hc_ss.shape == (40, R, L) and hc_bg.shape == (40, R)
+    tot = (hc_bg**2 + np.sum(hc_ss**2, axis=-1))
+    mean_exp = (number * h2fdf).sum(dim=(0, 1, 2)).cpu().numpy()
+    var_exp = (number * h2fdf * h2fdf).sum(dim=(0, 1, 2)).cpu().numpy()
+    zz = (tot.mean(axis=1) - mean_exp) / np.sqrt(var_exp / R)
+    assert np.all(np.abs(zz) < 5.0), zz
+    assert np.all(np.diff(hc_ss[0], axis=-1) <= 0)          # slots follow the rank order at f0
+    # the union of two half-runs with global realization offsets is the full run, bit for bit
+    lo = sam.gwb(fobs_edges, hard, realize=R // 2, loudest=L, seed=77, r0=0)
+    hi = sam.gwb(fobs_edges, hard, realize=R // 2, loudest=L, seed=77, r0=R // 2)
+    assert np.array_equal(np.concatenate([lo[0], hi[0]], axis=1), hc_ss)
+    assert np.array_equal(np.concatenate([lo[1], hi[1]], axis=1), hc_bg)
