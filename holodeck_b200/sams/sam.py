@@ -16,22 +16,19 @@ Device-resident intermediates (density, merger times, the (M,Q,Z,F) grids) never
 ``gwb``; numpy copies of ``static_binary_density``, ``_gmt_time`` and ``_redz_prime`` are made lazily
 on first attribute access so user code that reads them keeps working.
 
-Known host-resident stage: the M-Mbulge scatter (``add_scatter_to_masses``, ``sam.py:1291-1394``) is
-scipy Delaunay / Clough-Tocher interpolation in the reference and is executed the same way here, on
-the host, between K0 and the stalled-bin zeroing -- it is row N1 of SURVEY.md section 8f ("next"),
-runs once per SAM, and is not part of the realization hot path.
+The M-Mbulge scatter (``add_scatter_to_masses``, ``sam.py:1291-1394``; row N1 of SURVEY.md section 8f) runs on
+the device too (``sams/scatter.py`` + K6): only its data-independent geometry (the Delaunay triangulation scipy
+builds inside ``CloughTocher2DInterpolator``) is prepared on the host, once per grid.
 """
 import ctypes as C
 from datetime import datetime
 
 import numpy as np
-import scipy as sp
-import scipy.interpolate   # noqa
-import scipy.stats   # noqa
 
 import holodeck_b200 as holo
 from holodeck_b200 import _lib, cosmo, utils, log, host_relations
 from holodeck_b200.constants import SPLC, MSOL, MPC
+from holodeck_b200.sams.scatter import add_scatter_to_masses   # noqa: F401  (module-level name, as in the reference)
 from holodeck_b200.sams.components import (
     _Galaxy_Pair_Fraction, _Galaxy_Stellar_Mass_Function, _Galaxy_Merger_Time, _Galaxy_Merger_Rate,
     GSMF_Schechter, GSMF_Double_Schechter, GPF_Power_Law, GMT_Power_Law, GMR_Illustris
@@ -252,9 +249,10 @@ class Semi_Analytic_Model:
             dur = datetime.now()
             dens_host = _lib.to_host(dens)
             mass_bef = self._integrated_binary_density(dens_host, sum=True)
-            self._dens_bef = np.copy(dens_host)
-            dens_host = add_scatter_to_masses(self.mtot, self.mrat, dens_host, scatter, log=log)
-            self._dens_aft = np.copy(dens_host)
+            self._dens_bef = dens_host
+            dens = add_scatter_to_masses(self.mtot, self.mrat, dens, scatter, log=log)     # device (K6)
+            dens_host = _lib.to_host(dens)
+            self._dens_aft = dens_host
             mass_aft = self._integrated_binary_density(dens_host, sum=True)
             dur = datetime.now() - dur
             dm = (mass_aft - mass_bef) / mass_bef
@@ -263,7 +261,6 @@ class Semi_Analytic_Model:
             log.info(f"\t{msg}")
             if np.fabs(dm) > 0.2:
                 log.error(f"Warning, significant change in number-mass!  {msg}")
-            dens = _lib.to_dev(dens_host)
 
         # set values after redshift zero to have zero density   (sam.py:392-394)
         if has_gmt:
@@ -459,88 +456,3 @@ def evolve_eccen_uniform_single(sam, eccen_init, sepa_init, nsteps):
         e1 = np.clip(e1, 0.0, None)
         eccen[step] = e1
     return sepa, eccen
-
-
-# ---- M-Mbulge scatter (host, scipy -- see module docstring; reference sam.py:1291-1394, utils.py:382-488)
-
-def _roll_rows(arr, roll_num):
-    roll = np.asarray(roll_num)
-    assert np.ndim(arr) == 2 and np.ndim(roll) == 1
-    nrows, ncols = arr.shape
-    assert roll.size == nrows
-    arr_roll = arr[:, [*range(ncols), *range(ncols-1)]].copy()
-    strd_0, strd_1 = arr_roll.strides
-    result = np.lib.stride_tricks.as_strided(arr_roll, (nrows, ncols, ncols), (strd_0, strd_1, strd_1))
-    return result[np.arange(nrows), (ncols - roll) % ncols]
-
-
-def _get_scatter_weights(uniform_cents, dist):
-    num = uniform_cents.size
-    dx = np.diff(uniform_cents)
-    if not np.allclose(dx, dx[0]):
-        err = "`get_scatter_weights` only works if `uniform_cents` are uniformly spaced!"
-        log.exception(err)
-        raise ValueError(err)
-    dx = dx[0]
-    dx = dx/2.0 + np.arange(num) * dx
-    dx = np.concatenate([-dx[::-1], dx])
-    return np.diff(dist.cdf(dx))
-
-
-def _get_rolled_weights(log_cents, dist):
-    num = log_cents.size
-    weights = _get_scatter_weights(log_cents, dist)
-    weights = weights[np.newaxis, :] * np.ones((num, weights.size))
-    roll = 1 - num + np.arange(num)
-    weights = _roll_rows(weights, roll)
-    return weights[:, :num]
-
-
-def _scatter_with_weights(dens, weights, axis=0):
-    dens = np.moveaxis(dens, axis, 0)
-    dens_new = np.einsum("j...,jk...", dens, weights)
-    return np.moveaxis(dens_new, 0, axis)
-
-
-def add_scatter_to_masses(mtot, mrat, dens, scatter, refine=4, log=None):
-    """Add the given scatter [dex] to masses m1 and m2 of a (M, Q, Z) density grid (``sam.py:1291-1394``).
-
-    (1) interpolate each z-slice onto a regular (log m1, log m2) grid (Clough-Tocher, nearest-neighbour
-    fill of bad values), (2) convolve along each axis with binned normal weights, (3) interpolate back.
-    """
-    if log is None:
-        log = holo.log
-    assert np.ndim(dens) == 3
-    assert np.shape(dens)[:2] == (mtot.size, mrat.size)
-    dist = sp.stats.norm(loc=0.0, scale=scatter)
-    output = np.zeros_like(dens)
-    m1, m2 = utils.m1m2_from_mtmr(mtot[:, np.newaxis], mrat[np.newaxis, :])
-    grid_size = m1.shape[0] * refine
-    mextr = utils.minmax([0.9*mtot[0]*mrat[0]/(1.0 + mrat[0]), mtot[-1]*(1.0 + mrat[0])/mrat[0]])
-    mgrid_log10 = np.log10(np.logspace(*np.log10(mextr), grid_size))
-    points0 = tuple([np.log10(mm.flatten()) for mm in (m1, m2)])
-    m1m2_grid = np.meshgrid(mgrid_log10, mgrid_log10, indexing='ij')
-    dlay = None
-    weights = _get_rolled_weights(mgrid_log10, dist)
-    for ii in range(np.shape(dens)[2]):
-        dens_redz = dens[:, :, ii]
-        points = points0 if dlay is None else dlay
-        interp = sp.interpolate.CloughTocher2DInterpolator(points, dens_redz.flatten())
-        m1m2_dens = interp(tuple(m1m2_grid))
-        if dlay is None:
-            dlay = interp.tri
-        bads = np.isnan(m1m2_dens) | (m1m2_dens < 0.0)
-        if np.any(bads):
-            interp = sp.interpolate.NearestNDInterpolator(points, dens_redz.flatten())
-            temp = interp(tuple(m1m2_grid))
-            m1m2_dens[bads] = temp[bads]
-            bads = np.isnan(m1m2_dens) | (m1m2_dens < 0.0)
-            if np.any(bads):
-                err = f"After 0th order interpolation, {utils.frac_str(bads)} remain!"
-                log.exception(err)
-                raise ValueError(err)
-        m1m2_dens = _scatter_with_weights(m1m2_dens, weights, axis=0)
-        m1m2_dens = _scatter_with_weights(m1m2_dens, weights, axis=1)
-        interp = sp.interpolate.RegularGridInterpolator((mgrid_log10, mgrid_log10), m1m2_dens)
-        output[:, :, ii] = interp(points0, method='linear').reshape(m1.shape)
-    return output

@@ -1,0 +1,237 @@
+"""M-Mbulge scatter of the binary density on the device (reference ``sams/sam.py:1291-1394``).
+
+``add_scatter_to_masses`` keeps the reference's signature and procedure:
+
+1. interpolate every redshift slice of ``dens`` from the irregular ``(log10 m1, log10 m2)`` images of the
+   ``(mtot, mrat)`` grid onto a regular ``G x G`` grid (Clough-Tocher, ``G = refine * M``), replacing NaN /
+   negative values by the nearest data point's value;
+2. redistribute with binned normal weights (``utils._get_rolled_weights``; as the reference's two
+   ``_scatter_with_weights`` calls actually do: twice along the primary-mass axis, see below);
+3. interpolate (bilinear) back to the original grid points.
+
+What depends on the *geometry* only -- the Delaunay triangulation, the location of the regular-grid points
+in it, nearest vertices, the normal matrices of scipy's gradient estimator and the dependency levels of its
+Gauss-Seidel sweep, the scatter weights -- is computed once per ``(mtot, mrat, refine, scatter)`` on the
+host (scipy.spatial, as the reference does inside ``CloughTocher2DInterpolator``) and cached: every SAM of
+a library shares it.  All data-dependent arithmetic runs on the GPU for the Z slices at once
+(``csrc/holo_scatter.cu``: K6a gradients, K6b Clough-Tocher + fill, K6c bilinear; the scatter product
+is one cuBLAS DGEMM on the ``(G, G*Z)`` layout).  There is no CPU path for the data.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib, utils
+
+__all__ = ["add_scatter_to_masses", "scatter_geometry"]
+
+_GEO_CACHE = {}
+_GEO_DTYPE = np.dtype([("simplex", "i4"), ("nearest", "i4"), ("v", "i4", 3), ("pad", "i4"),
+                       ("b", "f8", 3), ("e", "f8", 6), ("g", "f8", 3)])
+
+
+def _roll_rows(arr, roll_num):
+    """utils.roll_rows, utils.py:382-413"""
+    roll = np.asarray(roll_num)
+    nrows, ncols = arr.shape
+    arr_roll = arr[:, [*range(ncols), *range(ncols-1)]].copy()
+    strd_0, strd_1 = arr_roll.strides
+    result = np.lib.stride_tricks.as_strided(arr_roll, (nrows, ncols, ncols), (strd_0, strd_1, strd_1))
+    return result[np.arange(nrows), (ncols - roll) % ncols]
+
+
+def _get_scatter_weights(uniform_cents, dist):
+    """utils.get_scatter_weights, utils.py:416-452"""
+    num = uniform_cents.size
+    dx = np.diff(uniform_cents)
+    if not np.allclose(dx, dx[0]):
+        raise ValueError("`get_scatter_weights` only works if `uniform_cents` are uniformly spaced!")
+    dx = dx[0]
+    dx = dx/2.0 + np.arange(num) * dx
+    dx = np.concatenate([-dx[::-1], dx])
+    return np.diff(dist.cdf(dx))
+
+
+def _get_rolled_weights(log_cents, dist):
+    """utils._get_rolled_weights, utils.py:464-488"""
+    num = log_cents.size
+    weights = _get_scatter_weights(log_cents, dist)
+    weights = weights[np.newaxis, :] * np.ones((num, weights.size))
+    roll = 1 - num + np.arange(num)
+    weights = _roll_rows(weights, roll)
+    return weights[:, :num]
+
+
+def _dependency_levels(indptr, indices, npts):
+    """Level of every vertex in the dependency graph of an index-ordered Gauss-Seidel sweep: a vertex can be
+    updated once all its lower-numbered neighbours have been.  Returns (order, level_ptr)."""
+    level = np.zeros(npts, dtype=np.int64)
+    for ip in range(npts):
+        nb = indices[indptr[ip]:indptr[ip+1]]
+        lo = nb[nb < ip]
+        level[ip] = 0 if lo.size == 0 else level[lo].max() + 1
+    order = np.argsort(level, kind="stable").astype(np.int32)      # within a level: ascending vertex index
+    nlev = int(level.max()) + 1
+    level_ptr = np.zeros(nlev + 1, dtype=np.int32)
+    np.cumsum(np.bincount(level, minlength=nlev), out=level_ptr[1:])
+    return order, level_ptr
+
+
+def scatter_geometry(mtot, mrat, refine=4):
+    """Host-side, data-independent set-up for one ``(mtot, mrat)`` grid (cached by the caller)."""
+    import scipy.spatial
+    mtot = np.asarray(mtot, dtype=np.float64)
+    mrat = np.asarray(mrat, dtype=np.float64)
+    # primary / secondary masses of the grid points and the regular grid, sam.py:1339-1354
+    m1, m2 = utils.m1m2_from_mtmr(mtot[:, np.newaxis], mrat[np.newaxis, :])
+    grid_size = m1.shape[0] * refine
+    mextr = utils.minmax([0.9*mtot[0]*mrat[0]/(1.0 + mrat[0]), mtot[-1]*(1.0 + mrat[0])/mrat[0]])
+    mgrid_log10 = np.log10(np.logspace(*np.log10(mextr), grid_size))
+    pts = np.stack([np.log10(m1.flatten()), np.log10(m2.flatten())], axis=1)
+    npts = pts.shape[0]
+
+    # the triangulation CloughTocher2DInterpolator builds (scipy.spatial.Delaunay of the unscaled points)
+    tri = scipy.spatial.Delaunay(pts)
+    indptr, indices = tri.vertex_neighbor_vertices
+    indptr = np.asarray(indptr, dtype=np.int32)
+    indices = np.asarray(indices, dtype=np.int32)
+
+    # gradient estimator (interpnd.pyx `_estimate_gradients_2d_global`): per directed edge ex, ey, L^3 and per
+    # vertex the 2x2 normal matrix, accumulated in the neighbour order scipy uses
+    src = np.repeat(np.arange(npts), np.diff(indptr))
+    ex = pts[indices, 0] - pts[src, 0]
+    ey = pts[indices, 1] - pts[src, 1]
+    L = np.sqrt(ex**2 + ey**2)
+    L3 = L*L*L
+    edge = np.ascontiguousarray(np.stack([ex, ey, L3], axis=1))
+    qmat = np.zeros((npts, 4))
+    q0, q1, q3 = 4*ex*ex / L3, 4*ex*ey / L3, 4*ey*ey / L3
+    for ip in range(npts):          # sequential sums, as the C loop
+        a, b = indptr[ip], indptr[ip+1]
+        s0 = s1 = s3 = 0.0
+        for jp in range(a, b):
+            s0 += q0[jp]
+            s1 += q1[jp]
+            s3 += q3[jp]
+        qmat[ip] = (s0, s1, s3, s0*s3 - s1*s1)
+    order, level_ptr = _dependency_levels(indptr, indices, npts)
+
+    # regular-grid points: simplex, barycentric coordinates, nearest data point
+    gx, gy = np.meshgrid(mgrid_log10, mgrid_log10, indexing='ij')
+    xi = np.stack([gx.ravel(), gy.ravel()], axis=1)
+    isimp = tri.find_simplex(xi)
+    inside = isimp >= 0
+    geo = np.zeros(xi.shape[0], dtype=_GEO_DTYPE)
+    geo["simplex"] = isimp
+    geo["nearest"] = scipy.spatial.cKDTree(pts).query(xi)[1]
+    sidx = isimp[inside]
+    T = tri.transform[sidx]
+    c01 = np.einsum('tij,tj->ti', T[:, :2, :], xi[inside] - T[:, 2, :])
+    geo["b"][inside] = np.concatenate([c01, 1.0 - c01.sum(axis=1, keepdims=True)], axis=1)
+    S = tri.simplices
+    P = tri.points
+    geo["v"][inside] = S[sidx]
+    e12 = P[S[:, 1]] - P[S[:, 0]]
+    e23 = P[S[:, 2]] - P[S[:, 1]]
+    e31 = P[S[:, 0]] - P[S[:, 2]]
+    geo["e"][inside] = np.concatenate([e12, e23, e31], axis=1)[sidx]
+    # affine-invariant edge parameters from the neighbours' centroids (interpnd.pyx `_clough_tocher_2d_single`)
+    gpar = np.full((S.shape[0], 3), -0.5)
+    cent = (P[S[:, 0]] + P[S[:, 1]] + P[S[:, 2]]) / 3
+    for kk in range(3):
+        itri = tri.neighbors[:, kk]
+        ok = itri != -1
+        dd = cent[itri[ok]] - tri.transform[ok, 2, :]
+        cc = np.einsum('tij,tj->ti', tri.transform[ok, :2, :], dd)
+        cc = np.concatenate([cc, 1.0 - cc.sum(axis=1, keepdims=True)], axis=1)
+        i1, i2 = [(2, 1), (0, 2), (1, 0)][kk]
+        gpar[ok, kk] = (2*cc[:, i1] + cc[:, i2] - 1) / (2 - 3*cc[:, i1] - 3*cc[:, i2])
+    geo["g"][inside] = gpar[sidx]
+
+    # RegularGridInterpolator(method='linear') back to the data points: cell index and normalised distance
+    def find(xx):
+        ii = np.searchsorted(mgrid_log10, xx) - 1
+        ii = np.clip(ii, 0, grid_size - 2)
+        return ii.astype(np.int32), (xx - mgrid_log10[ii]) / (mgrid_log10[ii+1] - mgrid_log10[ii])
+    if (pts.min() < mgrid_log10[0]) or (pts.max() > mgrid_log10[-1]):
+        raise ValueError("One of the requested xi is out of bounds")     # RegularGridInterpolator(bounds_error=True)
+    i0, y0 = find(pts[:, 0])
+    i1, y1 = find(pts[:, 1])
+    # what the kernel reads: per-edge quotients and the inverse normal matrices (geometry only)
+    edge4 = np.ascontiguousarray(np.stack([ex, ey, ex / L3, ey / L3], axis=1))
+    det = qmat[:, 3]
+    qinv = np.ascontiguousarray(np.stack([qmat[:, 2] / det, -qmat[:, 1] / det, -qmat[:, 1] / det, qmat[:, 0] / det], axis=1))
+    return dict(npts=npts, G=grid_size, mgrid_log10=mgrid_log10, points=pts, indptr=indptr, indices=indices, edge=edge,
+                qmat=qmat, edge4=edge4, qinv=qinv, order=order, level_ptr=level_ptr, geo=geo, i0=i0, i1=i1, y0=y0, y1=y1, tri=tri)
+
+
+def _device_geometry(mtot, mrat, refine):
+    import torch
+    key = (np.asarray(mtot).tobytes(), np.asarray(mrat).tobytes(), int(refine), torch.cuda.current_device())
+    hit = _GEO_CACHE.get(key)
+    if hit is None:
+        gg = scatter_geometry(mtot, mrat, refine)
+        lib = _lib.load()
+        assert lib.holo_scatter_geo_bytes() == _GEO_DTYPE.itemsize
+        dev = dict(npts=gg["npts"], G=gg["G"], mgrid_log10=gg["mgrid_log10"], nlevels=int(gg["level_ptr"].size - 1))
+        for name in ("indptr", "indices", "order", "level_ptr", "i0", "i1"):
+            dev[name] = _lib.to_dev(gg[name], dtype=torch.int32)
+        for name in ("edge4", "qinv", "y0", "y1"):
+            dev[name] = _lib.to_dev(gg[name])
+        dev["geo"] = torch.from_numpy(gg["geo"].view(np.uint8).copy()).to(_lib.device())
+        if len(_GEO_CACHE) > 8:
+            _GEO_CACHE.clear()
+        _GEO_CACHE[key] = hit = dev
+    return hit
+
+
+def add_scatter_to_masses(mtot, mrat, dens, scatter, refine=4, log=None):
+    """Add the given scatter [dex] to masses m1 and m2 of a ``(M, Q, Z)`` density grid (``sam.py:1291-1394``).
+
+    ``dens`` may be a numpy array (numpy is returned, as the reference) or a CUDA tensor (a CUDA tensor is returned).
+    """
+    import scipy.stats
+    import torch
+    lib = _lib.require_gpu()
+    on_dev = _lib.is_device_array(dens)
+    assert dens.ndim == 3
+    assert tuple(dens.shape[:2]) == (np.size(mtot), np.size(mrat))
+    M, Q, Z = (int(ss) for ss in dens.shape)
+    gg = _device_geometry(mtot, mrat, refine)
+    npts, G = gg["npts"], gg["G"]
+    data = _lib.to_dev(dens).reshape(npts, Z)
+    # The two calls `_scatter_with_weights(.., axis=0)` and `(.., axis=1)` of the reference (sam.py:1383-1384) both
+    # contract the PRIMARY-mass axis: `np.einsum("j...,jk...")` is in implicit mode, so its output is ordered
+    # (..., k) -- the first call returns the scattered array transposed, the `moveaxis(.., 1, 0)` of the second call
+    # brings the primary axis back to the front, and it is scattered again (utils.py:455-461).  The net operator
+    # is  F = (W W)^T A  along axis 0, nothing along axis 1; reproduced as one DGEMM with the cached product.
+    wkey = ("weights", float(scatter))
+    if wkey not in gg:
+        dist = scipy.stats.norm(loc=0.0, scale=scatter)
+        ww = _get_rolled_weights(gg["mgrid_log10"], dist)
+        gg[wkey] = _lib.to_dev(np.ascontiguousarray((ww @ ww).T))
+    w2t = gg[wkey]
+
+    grad = _lib.empty((npts, 2, Z))
+    niter = torch.empty(Z, dtype=torch.int32, device=data.device)
+    rc = lib.holo_scatter_gradients(npts, Z, _lib.ptr(gg["indptr"]), _lib.ptr(gg["indices"]), _lib.ptr(gg["edge4"]),
+                                    _lib.ptr(gg["qinv"]), _lib.ptr(gg["order"]), _lib.ptr(gg["level_ptr"]), gg["nlevels"],
+                                    _lib.ptr(data), 400, 1e-6, _lib.ptr(grad), _lib.ptr(niter), _lib.stream())
+    _lib.check(rc, "add_scatter_to_masses (gradients)")
+    grid = _lib.empty((G, G, Z))
+    flags = torch.zeros(1, dtype=torch.int32, device=data.device)
+    rc = lib.holo_scatter_ct_eval(G * G, Z, _lib.ptr(gg["geo"]), _lib.ptr(data), _lib.ptr(grad), _lib.ptr(grid),
+                                  _lib.ptr(flags), _lib.stream())
+    _lib.check(rc, "add_scatter_to_masses (interpolation)")
+    grid = torch.matmul(w2t, grid.reshape(G, G * Z))          # (G, G*Z): cuBLAS DGEMM, new[k, ...] = sum_j (WW)[j, k] A[j, ...]
+    out = _lib.empty((npts, Z))
+    rc = lib.holo_scatter_bilinear(npts, G, Z, _lib.ptr(gg["i0"]), _lib.ptr(gg["i1"]), _lib.ptr(gg["y0"]), _lib.ptr(gg["y1"]),
+                                   _lib.ptr(grid), _lib.ptr(out), _lib.stream())
+    _lib.check(rc, "add_scatter_to_masses (back-interpolation)")
+    if int(flags.item()) != 0:
+        err = "After 0th order interpolation, bad values remain!"        # sam.py:1376-1380
+        if log is not None:
+            log.exception(err)
+        raise ValueError(err)
+    out = out.reshape(M, Q, Z)
+    return out if on_dev else _lib.to_host(out)

@@ -290,6 +290,41 @@ int holo_sam_calc_gwb_single_eccen(holo_cy_consts cc /* cyutils.pyx:47 GW_DADT_S
                                    int64_t workspace_bytes, void* stream);
 int64_t holo_eccen_workspace_bytes(int M, int Q, int Z, int F, int nharms, int nreals);
 
+/* ---------------------------------------------------------------------------------------------
+ * K6  M-Mbulge scatter of the binary density.  Replaces the per-redshift scipy pipeline of
+ *      add_scatter_to_masses  holodeck/sams/sam.py:1291-1394 (with utils.py:416-488):
+ *      CloughTocher2DInterpolator + NearestNDInterpolator fill -> two dense scatter products ->
+ *      RegularGridInterpolator(linear).  The geometry (Delaunay triangulation of the (log10 m1, log10 m2)
+ *      images of the grid, point location, level schedule of the Gauss-Seidel sweep) is data-independent and
+ *      prepared once per grid by the host driver (holodeck_b200/sams/scatter.py); the two products are plain
+ *      DGEMMs (cuBLAS) between `holo_scatter_ct_eval` and `holo_scatter_bilinear`.
+ *      Layouts: density (npts = M*Q, Z) z fastest; gradients (npts, 2, Z); regular grid (G, G, Z).
+ * ------------------------------------------------------------------------------------------- */
+
+/* gradients at the triangulation vertices: scipy interpnd `_estimate_gradients_2d_global` (Gauss-Seidel,
+ * maxiter / tol as CloughTocher2DInterpolator: 400, 1e-6), all Z slices at once.
+ * indptr/indices: Delaunay.vertex_neighbor_vertices; edge (nnz,4): ex, ey, ex/L^3, ey/L^3 per directed edge;
+ * qinv (npts,4): inverse of the vertex's 2x2 normal matrix; order/level_ptr: vertices grouped by dependency level.
+ * niter (Z,) (may be NULL): sweeps used, 0 = not converged. */
+int holo_scatter_gradients(int npts, int Z, const int* indptr, const int* indices, const double* edge,
+                           const double* qinv, const int* order, const int* level_ptr, int nlevels,
+                           const double* data, int maxiter, double tol, double* grad, int* niter,
+                           void* stream);
+
+/* Clough-Tocher values at `ngrid` regular-grid points (geometry records of holo_scatter_geo_bytes() bytes
+ * each: simplex, nearest vertex, vertices, barycentric coordinates, edge vectors, g[3]); NaN (outside the
+ * hull) and negative values take the nearest vertex's value (sam.py:1370-1375); flags[0] != 0 if a bad
+ * value survives (sam.py:1376-1380 raises ValueError). */
+int holo_scatter_ct_eval(int64_t ngrid, int Z, const void* geo, const double* data, const double* grad,
+                         double* out, int* flags, void* stream);
+
+/* RegularGridInterpolator(method='linear') from the (G, G, Z) grid back to the npts data points:
+ * i0/i1 lower cell indices, y0/y1 normalised distances. */
+int holo_scatter_bilinear(int npts, int G, int Z, const int* i0, const int* i1, const double* y0,
+                          const double* y1, const double* grid, double* out, void* stream);
+
+int holo_scatter_geo_bytes(void);
+
 #ifdef __cplusplus
 }
 #endif
