@@ -209,15 +209,15 @@ def workload_config(args):
 # B200 arm
 # ==================================================================================================
 
-def make_models(args):
-    """Fresh SAM + hardening for configs[1] (librarian/param_spaces_classic.py:13-89, scatter off)."""
+def make_models(args, scatter_dex=0.0):
+    """Fresh SAM + hardening for configs[1] (librarian/param_spaces_classic.py:13-89; M-Mbulge scatter off unless asked)."""
     import holodeck_b200 as holo
     from holodeck_b200 import sams, host_relations
     from holodeck_b200.constants import GYR, PC
     gsmf = sams.GSMF_Schechter(phi0=-2.77, phiz=-0.6, mchar0_log10=11.24, mcharz=0.11, alpha0=-1.21, alphaz=-0.03)
     gpf = sams.GPF_Power_Law(frac_norm_allq=0.025, malpha=0.0, qgamma=0.0, zbeta=1.0, max_frac=1.0)
     gmt = sams.GMT_Power_Law(time_norm=0.5*GYR, malpha=0.0, qgamma=-1.0, zbeta=-0.5)
-    mmb = host_relations.MMBulge_KH2013(mamp_log10=8.69, mplaw=1.10, scatter_dex=0.0)
+    mmb = host_relations.MMBulge_KH2013(mamp_log10=8.69, mplaw=1.10, scatter_dex=scatter_dex)
     sam = sams.Semi_Analytic_Model(gsmf=gsmf, gpf=gpf, gmt=gmt, mmbulge=mmb, shape=tuple(args.shape))
     hard = holo.hardening.Fixed_Time_2PL_SAM(sam, 3.0*GYR, sepa_init=1e4*PC, rchar=100.0*PC, gamma_inner=-1.0,
                                              gamma_outer=+2.5)
@@ -309,6 +309,17 @@ def run_b200(args):
     assert out_e2e[0].shape == (args.nfreqs, R * world, L) and out_e2e[1].shape == (args.nfreqs, R * world)
     assert np.all(np.isfinite(out_e2e[1])) and np.all(out_e2e[1] > 0)
 
+    # ---- the same step with the PS_Classic M-Mbulge scatter (0.3 dex) switched on: K6 runs once per SAM between
+    #      the density kernel and the stalled-bin zeroing (reported beside the headline, which keeps
+    #      the scatter off in both arms so that rounds stay comparable)
+    def step_scatter():
+        sam, hard = make_models(args, scatter_dex=0.3)
+        hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0, device=True)
+        return gather(hc_ss), gather(hc_bg)
+    for _ in range(2):
+        step_scatter()
+    ms_scatter, _, _, _ = timed(step_scatter, args.steps)
+
     # ---- per-stage device times (CUDA events on the launching stream), one extra profiled pass
     stages = stage_times(args, fobs_edges, R, L, seed, r0)
 
@@ -372,6 +383,8 @@ def run_b200(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(n_launch),
         "loudest_retries": int(__import__("holodeck_b200").cyutils.STATS["loudest_retries"]),
+        "mmbulge_scatter_on": {"ms_per_step": ms_scatter / args.steps, "value": world * ncell * R * args.steps / (ms_scatter * 1e-3),
+                               "note": "same step with mmb_scatter_dex=0.3 (K6 on the device, once per SAM)"},
         "roofline": roofline,
         "stages_ms": {kk: round(vv, 4) for kk, vv in stages.items()},
         "kernels": per_kernel,

@@ -247,13 +247,11 @@ class Semi_Analytic_Model:
         if scatter > 0.0:
             log.info(f"Adding MMbulge scatter ({scatter:.4e})")
             dur = datetime.now()
-            dens_host = _lib.to_host(dens)
-            mass_bef = self._integrated_binary_density(dens_host, sum=True)
-            self._dens_bef = dens_host
+            mass_bef = self._integrated_binary_density_device(dens)
+            self._dens_bef_dev = dens
             dens = add_scatter_to_masses(self.mtot, self.mrat, dens, scatter, log=log)     # device (K6)
-            dens_host = _lib.to_host(dens)
-            self._dens_aft = dens_host
-            mass_aft = self._integrated_binary_density(dens_host, sum=True)
+            self._dens_aft_dev = dens.clone() if has_gmt else dens    # (the stalled bins are zeroed in place below)
+            mass_aft = self._integrated_binary_density_device(dens)
             dur = datetime.now() - dur
             dm = (mass_aft - mass_bef) / mass_bef
             log.info(f"Scatter added after {dur.total_seconds()} sec")
@@ -306,6 +304,24 @@ class Semi_Analytic_Model:
         if (self._redz_prime_host is None) and (self._redz_prime_dev is not None):
             self._redz_prime_host = _lib.to_host(self._redz_prime_dev)
         return self._redz_prime_host
+
+    def _integrated_binary_density_device(self, dens):
+        """`_integrated_binary_density(dens, sum=True)` for a device array (trapezoid over the three grid axes)."""
+        import torch
+        integ = torch.trapezoid(dens, _lib.to_dev(np.log10(self.mtot)), dim=0)
+        integ = torch.trapezoid(integ, _lib.to_dev(self.mrat), dim=0)
+        integ = torch.trapezoid(integ, _lib.to_dev(self.redz), dim=0)
+        return float(integ.item())
+
+    @property
+    def _dens_bef(self):
+        """Density before the M-Mbulge scatter was applied (``sam.py:374``), numpy."""
+        return None if getattr(self, "_dens_bef_dev", None) is None else _lib.to_host(self._dens_bef_dev)
+
+    @property
+    def _dens_aft(self):
+        """Density after the M-Mbulge scatter was applied (``sam.py:377``), numpy."""
+        return None if getattr(self, "_dens_aft_dev", None) is None else _lib.to_host(self._dens_aft_dev)
 
     def _integrated_binary_density(self, ndens=None, sum=True):
         """Integrate the binary number-density over the grid (``sam.py:678-703``; host numpy)."""
