@@ -174,6 +174,7 @@ SIGNATURES = {
     "holo_scatter_ct_eval": [_L, _I, _P, _P, _P, _P, _P, _P],
     "holo_scatter_bilinear": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "holo_scatter_geo_bytes": [],
+    "holo_model_details_hist": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
 }
 _RESTYPES = {
     "holo_last_error": C.c_char_p,

@@ -376,6 +376,80 @@ __global__ void expect_final_kernel(const double* __restrict__ partial, int nblk
     hc2[f] = s;
 }
 
+// -------------------------------------------------------------------------------------------------
+// K7: lib_tools._calc_model_details (librarian/lib_tools.py:904-939): per total-mass bin and frequency, the
+// strain-weighted and the plain number of binaries histogrammed over their FINAL redshift (cell-centre mean of
+// redz_final, sentinels included, as utils.midpoints does; bins = the SAM redshift edges, last bin closed;
+// scipy.stats.binned_statistic(..., statistic='sum')).
+// One CTA per (mass bin, group of 4 frequencies); thread <-> redshift bin.  The cells of one q row are staged
+// (bin index + the two values), then every thread gathers the cells that fall in ITS bin in (q, z) order:
+// no floating-point atomics, the sums are bit-reproducible.
+// -------------------------------------------------------------------------------------------------
+constexpr int DET_FG = 4;
+
+__global__ void __launch_bounds__(128)
+details_hist_kernel(BinGeom g, const double* __restrict__ redz_edges, const double* __restrict__ redz_final,
+                    const double* __restrict__ number, const double* __restrict__ h2fdf,
+                    double* __restrict__ gwb_hist /* (M-1, Z-1, F) */, double* __restrict__ num_hist) {
+    extern __shared__ unsigned char s_raw[];
+    const int Qb = g.Q - 1, Zb = g.Z - 1, F = g.F;
+    double* s_edges = reinterpret_cast<double*>(s_raw);           // (Z)
+    double* s_hv = s_edges + g.Z;                                 // (DET_FG, Zb) hc2 * number
+    double* s_nv = s_hv + DET_FG * Zb;                            // (DET_FG, Zb) number
+    int* s_bin = reinterpret_cast<int*>(s_nv + DET_FG * Zb);      // (DET_FG, Zb) bin index or -1
+    const int mm = blockIdx.x, f0 = blockIdx.y * DET_FG;
+    const int nf = (F - f0) < DET_FG ? (F - f0) : DET_FG;
+    const int64_t sZ = F, sQ = (int64_t)g.Z * F, sM = (int64_t)g.Q * g.Z * F;
+    for (int i = threadIdx.x; i < g.Z; i += blockDim.x) s_edges[i] = redz_edges[i];
+    double accg[DET_FG], accn[DET_FG];      // this thread's bin (threadIdx.x + k*blockDim.x handled by the outer loop)
+    for (int b0 = 0; b0 < Zb; b0 += blockDim.x) {
+        const int mybin = b0 + threadIdx.x;
+#pragma unroll
+        for (int fi = 0; fi < DET_FG; ++fi) { accg[fi] = 0.0; accn[fi] = 0.0; }
+        for (int qq = 0; qq < Qb; ++qq) {
+            __syncthreads();
+            for (int zz = threadIdx.x; zz < Zb; zz += blockDim.x) {
+                const int64_t base = mm * sM + qq * sQ + zz * sZ + f0;
+                const int64_t cell = (((int64_t)mm * Qb + qq) * Zb + zz) * F + f0;
+                for (int fi = 0; fi < nf; ++fi) {
+                    const double zc = corner_mean_redz(redz_final, sM, sQ, sZ, base + fi);
+                    int bin = -1;
+                    if (zc >= s_edges[0] && zc <= s_edges[g.Z - 1]) {
+                        int lo = 0, hi = g.Z - 1;                 // largest lo with edges[lo] <= zc
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (s_edges[mid] <= zc) lo = mid; else hi = mid;
+                        }
+                        bin = lo;                                 // zc == last edge lands in the last bin
+                    }
+                    const double nv = number[cell + fi];
+                    s_bin[fi * Zb + zz] = bin;
+                    s_nv[fi * Zb + zz] = nv;
+                    s_hv[fi * Zb + zz] = h2fdf[cell + fi] * nv;
+                }
+            }
+            __syncthreads();
+            if (mybin < Zb) {
+                for (int fi = 0; fi < nf; ++fi) {
+                    for (int zz = 0; zz < Zb; ++zz) {
+                        if (s_bin[fi * Zb + zz] == mybin) {
+                            accg[fi] += s_hv[fi * Zb + zz];
+                            accn[fi] += s_nv[fi * Zb + zz];
+                        }
+                    }
+                }
+            }
+        }
+        if (mybin < Zb) {
+            for (int fi = 0; fi < nf; ++fi) {
+                const int64_t o = ((int64_t)mm * Zb + mybin) * F + f0 + fi;
+                gwb_hist[o] = accg[fi];
+                num_hist[o] = accn[fi];
+            }
+        }
+    }
+}
+
 static int grid_for(int64_t n, int threads) {
     int64_t blocks = (n + threads - 1) / threads;
     int64_t cap = (int64_t)148 * 32;
@@ -566,6 +640,20 @@ int holo_gwb_expectation(const double* number, const double* h2fdf, int64_t ncel
     int rc = holo_check_launch("holo_gwb_expectation");
     cudaFreeAsync(partial, st);
     return rc;
+}
+
+int holo_model_details_hist(const double* redz_edges, const double* redz_final, const double* number,
+                            const double* h2fdf, int M, int Q, int Z, int F, double* gwb_hist, double* num_hist,
+                            void* stream) {
+    HOLO_REQUIRE(redz_edges && redz_final && number && h2fdf && gwb_hist && num_hist, "holo_model_details_hist: NULL argument");
+    HOLO_REQUIRE(M > 1 && Q > 1 && Z > 1 && F > 0, "holo_model_details_hist: bad shape");
+    BinGeom g{M, Q, Z, F};
+    const size_t smem = sizeof(double) * ((size_t)Z + 2 * DET_FG * (size_t)(Z - 1)) + sizeof(int) * DET_FG * (size_t)(Z - 1);
+    HOLO_REQUIRE(smem <= 48 * 1024, "holo_model_details_hist: too many redshift bins for shared memory");
+    dim3 grid(M - 1, (F + DET_FG - 1) / DET_FG);
+    details_hist_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(g, redz_edges, redz_final, number, h2fdf, gwb_hist, num_hist);
+    holo::count_launches(1);
+    return holo_check_launch("holo_model_details_hist");
 }
 
 }  // extern "C"

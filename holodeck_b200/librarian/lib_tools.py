@@ -14,7 +14,7 @@ import scipy as sp
 import scipy.stats   # noqa
 
 import holodeck_b200 as holo
-from holodeck_b200 import utils, cosmo
+from holodeck_b200 import utils, cosmo, _lib
 from holodeck_b200.constants import YR
 from holodeck_b200.librarian import (
     DEF_NUM_FBINS, DEF_NUM_LOUDEST, DEF_NUM_REALS, DEF_PTA_DUR, PSPACE_FILE_SUFFIX, FNAME_LIBRARY_SIM_FILE,
@@ -304,7 +304,8 @@ def run_model(
     Returns a dict with ``fobs_cents, fobs_edges`` and, depending on the flags, ``hc_ss (F,R,L)``,
     ``hc_bg (F,R)``, ``sspar (4,F,R,L)``, ``bgpar (7,F,R)``, ``gwb (F,R)``.  As in the reference the
     single-source split and the GWB use independent Poisson draws of the same number grid.
-    ``details_flag`` (SURVEY.md "next" row N4) is not provided.
+    ``details_flag`` adds ``static_binary_density, number, redz_final, gwb_params, num_params, gwb_mtot_redz_final,
+    num_mtot_redz_final`` (``_calc_model_details``, K7).
     """
     from holodeck_b200.sams import sam_cyutils
     from holodeck_b200 import gravwaves, single_sources
@@ -314,9 +315,6 @@ def run_model(
         if log is not None:
             log.exception(err)
         raise RuntimeError(err)
-    if details_flag:
-        raise NotImplementedError("`details_flag` (lib_tools._calc_model_details) is outside the GPU hot path")
-
     data = {}
     fobs_cents, fobs_edges = utils.pta_freqs(dur=pta_dur*YR, num=nfreqs)
     # convert from GW to orbital frequencies
@@ -338,6 +336,16 @@ def run_model(
     strain = gravwaves._char_strain_sq(edges, use_redz, params=bool(params_flag), dnum=diff_num)
     number = strain["number"]
     sub = None if seed is None else np.random.SeedSequence(seed).generate_state(2, dtype=np.uint64)
+    if details_flag:
+        data['static_binary_density'] = sam.static_binary_density
+        data['number'] = _lib.to_host(number)
+        data['redz_final'] = _lib.to_host(redz_final)
+        gwb_pars, num_pars, gwb_mtot_redz_final, num_mtot_redz_final = _calc_model_details(
+            edges, redz_final, number, _h2fdf=strain["h2fdf"])
+        data['gwb_params'] = gwb_pars
+        data['num_params'] = num_pars
+        data['gwb_mtot_redz_final'] = gwb_mtot_redz_final
+        data['num_mtot_redz_final'] = num_mtot_redz_final
 
     # calculate single sources and/or binary parameters
     if singles_flag or params_flag:
@@ -362,6 +370,41 @@ def run_model(
         data['gwb'] = gwb
 
     return data
+
+
+def _calc_model_details(edges, redz_final, number, _h2fdf=None):
+    """Derived properties of a population (``lib_tools.py:845-943``): strain-weighted and number-weighted
+    marginals over (mtot, mrat, redz) and their distributions over the *final* redshift.
+
+    Returns ``gwb_pars`` = [(M-1,Z-1,F), (Q-1,Z-1,F), (Z-1,F), (Z-1,F)], ``num_pars`` (same shapes),
+    ``gwb_mtot_redz_final (M-1,Z-1,F)``, ``num_mtot_redz_final (M-1,Z-1,F)`` as numpy arrays.  The marginals are
+    axis sums on the device; the ``2 F (1 + (M-1))`` ``scipy.stats.binned_statistic`` calls of the reference
+    are one histogram kernel (K7, ``holo_model_details_hist``).
+    """
+    import torch
+    from holodeck_b200 import gravwaves
+    lib = _lib.require_gpu()
+    redz = np.asarray(edges[2], dtype=np.float64)
+    rzf = _lib.to_dev(redz_final)
+    num = _lib.to_dev(number)
+    M, Q, Z, F = (int(ss) for ss in rzf.shape)
+    assert tuple(num.shape) == (M - 1, Q - 1, Z - 1, F)
+    # (M-1, Q-1, Z-1, F) characteristic-strain squared for each bin
+    hc2 = _h2fdf if _h2fdf is not None else gravwaves._char_strain_sq(edges, rzf, params=False)["h2fdf"]
+    hc2_num = hc2 * num                                    # strain-squared weighted number of binaries
+    denom = torch.sum(hc2_num, dim=(0, 1, 2))             # (F,) total GWB in each frequency bin
+    gwb_pars, num_pars = [], []
+    for margins in ((1,), (0,), (0, 1)):                  # lib_tools.py:876-900
+        gwb_pars.append(_lib.to_host(torch.sum(hc2_num, dim=margins) / denom))
+        num_pars.append(_lib.to_host(torch.sum(num, dim=margins)))
+    gwb_hist = _lib.empty((M - 1, Z - 1, F))
+    num_hist = _lib.empty((M - 1, Z - 1, F))
+    rc = lib.holo_model_details_hist(_lib.ptr(_lib.to_dev(redz)), _lib.ptr(rzf), _lib.ptr(num), _lib.ptr(hc2), M, Q, Z, F,
+                                     _lib.ptr(gwb_hist), _lib.ptr(num_hist), _lib.stream())
+    _lib.check(rc, "_calc_model_details")
+    gwb_pars.append(_lib.to_host(torch.sum(gwb_hist, dim=0) / denom))       # all mass bins together, lib_tools.py:913-923
+    num_pars.append(_lib.to_host(torch.sum(num_hist, dim=0)))
+    return gwb_pars, num_pars, _lib.to_host(gwb_hist / denom), _lib.to_host(num_hist)
 
 
 def _get_sim_fname(path, pnum, library=True):

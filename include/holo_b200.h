@@ -291,6 +291,18 @@ int holo_sam_calc_gwb_single_eccen(holo_cy_consts cc /* cyutils.pyx:47 GW_DADT_S
 int64_t holo_eccen_workspace_bytes(int M, int Q, int Z, int F, int nharms, int nreals);
 
 /* ---------------------------------------------------------------------------------------------
+ * K7  Library "details" (SURVEY 8f N4).  Replaces the 2 x F x (1 + (M-1)) scipy.stats.binned_statistic calls of
+ *      lib_tools._calc_model_details  holodeck/librarian/lib_tools.py:904-939:
+ *      gwb_hist[m, b, f] = sum over (q, z) cells of mass bin m whose cell-centre final redshift falls in
+ *      redshift bin b of  h2fdf * number ;  num_hist the same for `number`  (bins [e_b, e_b+1), last closed).
+ *      The marginals of lib_tools.py:876-900 are plain axis sums (host driver, torch.sum).
+ * ------------------------------------------------------------------------------------------- */
+int holo_model_details_hist(const double* redz_edges /* (Z,) */, const double* redz_final /* (M,Q,Z,F) */,
+                            const double* number /* (M-1,Q-1,Z-1,F) */, const double* h2fdf,
+                            int M, int Q, int Z, int F, double* gwb_hist /* (M-1,Z-1,F) */,
+                            double* num_hist, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K6  M-Mbulge scatter of the binary density.  Replaces the per-redshift scipy pipeline of
  *      add_scatter_to_masses  holodeck/sams/sam.py:1291-1394 (with utils.py:416-488):
  *      CloughTocher2DInterpolator + NearestNDInterpolator fill -> two dense scatter products ->

@@ -771,3 +771,46 @@ def evolve_eccen_uniform_single(mtot_edges, eccen_init, sepa_init, nsteps):
         e1 = np.clip(e1, 0.0, None)
         eccen[step] = e1
     return sepa, eccen
+
+
+# ---- librarian "details": lib_tools._calc_model_details, librarian/lib_tools.py:845-943
+
+def calc_model_details(edges, redz_final, number, hc2):
+    """lib_tools._calc_model_details lib_tools.py:866-943 given hc2 = char_strain_sq_from_bin_edges_redz(edges, redz_final)"""
+    redz = edges[2]
+    nmbins = len(edges[0]) - 1
+    nzbins = len(redz) - 1
+    nfreqs = len(edges[3]) - 1
+    hc2_num = hc2 * number
+    denom = np.sum(hc2_num, axis=(0, 1, 2))
+    gwb_pars = []
+    num_pars = []
+    for ii in range(3):
+        margins = [0, 1]
+        if ii in margins:
+            del margins[ii]
+        margins = tuple(margins)
+        gwb_pars.append(np.sum(hc2_num, axis=margins) / denom)
+        num_pars.append(np.sum(number, axis=margins))
+    rz = redz_final.copy()
+    for ii in range(3):
+        rz = midpoints(rz, axis=ii)
+    gwb_mtot_redz_final = np.zeros((nmbins, nzbins, nfreqs))
+    num_mtot_redz_final = np.zeros((nmbins, nzbins, nfreqs))
+    gwb_rz = np.zeros((nzbins, nfreqs))
+    num_rz = np.zeros((nzbins, nfreqs))
+    for ii in range(nfreqs):
+        rz_flat = rz[:, :, :, ii].flatten()
+        numer, *_ = sp.stats.binned_statistic(rz_flat, hc2_num[:, :, :, ii].flatten(), bins=redz, statistic='sum')
+        gwb_rz[:, ii] = numer / denom[ii]
+        tpar, *_ = sp.stats.binned_statistic(rz_flat, number[:, :, :, ii].flatten(), bins=redz, statistic='sum')
+        num_rz[:, ii] = tpar
+        for mm in range(nmbins):
+            rz_flat = rz[mm, :, :, ii].flatten()
+            numer, *_ = sp.stats.binned_statistic(rz_flat, hc2_num[mm, :, :, ii].flatten(), bins=redz, statistic='sum')
+            gwb_mtot_redz_final[mm, :, ii] = numer / denom[ii]
+            tpar, *_ = sp.stats.binned_statistic(rz_flat, number[mm, :, :, ii].flatten(), bins=redz, statistic='sum')
+            num_mtot_redz_final[mm, :, ii] = tpar
+    gwb_pars.append(gwb_rz)
+    num_pars.append(num_rz)
+    return gwb_pars, num_pars, gwb_mtot_redz_final, num_mtot_redz_final

@@ -131,3 +131,39 @@ def test_realizer_sam_weights():
     assert len(w2) == 3 and all(len(ss[0]) == len(ww) for ss, ww in zip(s2, w2))
     with pytest.raises(ValueError):
         holo.extensions.Realizer_SAM(fobs_edges / 2.0)
+
+
+def test_model_details_match_reference_procedure():
+    """run_model(details_flag=True) / _calc_model_details against the reference procedure
+    (oracle/glue.calc_model_details: numpy sums + scipy.stats.binned_statistic, lib_tools.py:845-943)."""
+    import holodeck_b200 as holo
+    from holodeck_b200 import host_relations, librarian
+    from holodeck_b200.librarian import lib_tools
+    from holodeck_b200.constants import GYR, PC
+    from oracle import glue
+    from conftest import rel_err
+    sam = holo.sams.Semi_Analytic_Model(shape=(17, 13, 21), gpf=holo.sams.GPF_Power_Law(), gmt=holo.sams.GMT_Power_Law(),
+                                        mmbulge=host_relations.MMBulge_KH2013(scatter_dex=0.0))
+    hard = holo.hardening.Fixed_Time_2PL_SAM(sam, 3.0*GYR, sepa_init=1e4*PC, rchar=100.0*PC, gamma_inner=-1.0, gamma_outer=2.5)
+    data = librarian.run_model(sam, hard, nfreqs=7, nreals=4, nloudest=2, gwb_flag=False, singles_flag=False,
+                               details_flag=True, seed=1)
+    for key in ("static_binary_density", "number", "redz_final", "gwb_params", "num_params", "gwb_mtot_redz_final",
+                "num_mtot_redz_final", "fobs_cents", "fobs_edges"):
+        assert key in data
+    number, redz_final = data["number"], data["redz_final"]
+    assert number.shape == (16, 12, 20, 7) and redz_final.shape == (17, 13, 21, 7)
+    edges = [sam.mtot, sam.mrat, sam.redz, data["fobs_edges"] / 2.0]
+    from holodeck_b200 import gravwaves
+    hc2 = gravwaves.char_strain_sq_from_bin_edges_redz(edges, redz_final)
+    ref = glue.calc_model_details(edges, redz_final, number, hc2)
+    got = (data["gwb_params"], data["num_params"], data["gwb_mtot_redz_final"], data["num_mtot_redz_final"])
+    shapes = [(16, 20, 7), (12, 20, 7), (20, 7), (20, 7)]
+    for kk in range(4):
+        assert got[0][kk].shape == shapes[kk] and got[1][kk].shape == shapes[kk]
+        assert rel_err(got[0][kk], ref[0][kk]) < 1e-12, (kk, rel_err(got[0][kk], ref[0][kk]))
+        assert rel_err(got[1][kk], ref[1][kk]) < 1e-12
+    assert rel_err(got[2], ref[2]) < 1e-12 and rel_err(got[3], ref[3]) < 1e-12
+    assert got[3].sum() > 0 and np.array_equal(got[3] == 0, ref[3] == 0)
+    # direct call with host arrays, as the reference signature
+    again = lib_tools._calc_model_details(edges, redz_final, number)
+    assert np.array_equal(again[2], got[2]) and np.array_equal(again[3], got[3])
