@@ -3,8 +3,8 @@
 parameter spaces (``param_spaces_classic.py``) and a GPU-sharded ``gen_lib`` (samples partitioned over
 ranks exactly as ``gen_lib.py:139-141,169`` does over MPI ranks; ``torch.distributed`` instead of mpi4py).
 
-Out of scope: ``combine`` (hdf5 merge), ``fit_spectra``,
-``posterior_populations``.
+``combine.sam_lib_combine`` merges the per-sample files.  Out of scope (SURVEY.md section 2a
+row 11): ``fit_spectra``, ``posterior_populations``.
 """
 
 __version__ = "1.3"
@@ -23,7 +23,7 @@ from holodeck_b200.librarian import lib_tools   # noqa: E402
 from holodeck_b200.librarian.lib_tools import (   # noqa: E402,F401
     _Param_Space, _Param_Dist, PD_Uniform, PD_Uniform_Log, PD_Normal, run_model,
 )
-from holodeck_b200.librarian import param_spaces_classic   # noqa: E402
+from holodeck_b200.librarian import param_spaces_classic, combine   # noqa: E402,F401
 from holodeck_b200.librarian.param_spaces_classic import (   # noqa: E402,F401
     PS_Classic_Phenom_Uniform, PS_Classic_Phenom_Astro_Extended, PS_Classic_GWOnly_Uniform,
 )

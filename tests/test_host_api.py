@@ -110,3 +110,50 @@ def test_param_space_and_sharding():
     assert ext.param_names[2] == "gsmf_phi0_log10"     # renamed from `gsmf_phi0` (lib_tools.py:24-26)
     with pytest.raises(RuntimeError):
         librarian.run_model(None, None, gwb_flag=False, singles_flag=False)
+
+
+def test_library_combine_contract(tmp_path):
+    """combine.sam_lib_combine (SURVEY 8f N2): per-sample npz files -> one library with the reference's datasets;
+    failure files become NaN rows (combine.py:204-205, 404-417)."""
+    import holodeck_b200 as holo
+    from holodeck_b200.librarian import combine, lib_tools, DIRNAME_LIBRARY_SIMS
+    space = holo.librarian.PS_Classic_Phenom_Uniform(nsamples=5, seed=3)
+    sims = tmp_path / DIRNAME_LIBRARY_SIMS
+    sims.mkdir()
+    space.save(tmp_path)
+    rng = np.random.default_rng(0)
+    F, R, L = 6, 4, 3
+    fc = np.arange(1, F + 1) / 5e8
+    fe = (np.arange(F + 1) + 0.5) / 5e8
+    want = {}
+    for pnum in range(5):
+        fname = lib_tools._get_sim_fname(sims, pnum)
+        if pnum == 2:
+            np.savez(fname, fail="boom")
+            continue
+        want[pnum] = dict(gwb=rng.uniform(size=(F, R)), hc_ss=rng.uniform(size=(F, R, L)), hc_bg=rng.uniform(size=(F, R)),
+                          sspar=rng.uniform(size=(4, F, R, L)), bgpar=rng.uniform(size=(7, F, R)))
+        np.savez(fname, fobs_cents=fc, fobs_edges=fe, params=space.param_samples[pnum], param_names=space.param_names, **want[pnum])
+    lib_path = combine.sam_lib_combine(tmp_path, holo.log)
+    assert lib_path.exists() and lib_path.stem == "sam-library"
+    if lib_path.suffix == ".npz":
+        lib = np.load(lib_path)
+        names = [nn.decode() for nn in lib["attrs/param_names"]]
+    else:
+        import h5py
+        lib = {kk: vv[()] for kk, vv in h5py.File(lib_path, "r").items()}
+        names = [nn.decode() for nn in h5py.File(lib_path, "r").attrs["param_names"]]
+    assert names == list(space.param_names)
+    assert lib["gwb"].shape == (5, F, R) and lib["hc_ss"].shape == (5, F, R, L) and lib["hc_bg"].shape == (5, F, R)
+    assert lib["sspar"].shape == (5, 4, F, R, L) and lib["bgpar"].shape == (5, 7, F, R)
+    assert np.array_equal(lib["fobs_cents"], fc) and np.array_equal(lib["fobs_edges"], fe)
+    for pnum, dd in want.items():
+        for kk, vv in dd.items():
+            assert np.array_equal(lib[kk][pnum], vv)
+        assert np.array_equal(lib["sample_params"][pnum], space.param_samples[pnum])
+    assert np.all(np.isnan(lib["gwb"][2])) and np.all(np.isnan(lib["hc_ss"][2])) and np.all(np.isnan(lib["sample_params"][2]))
+    assert combine.sam_lib_combine(tmp_path, holo.log) is None                      # exists: not recreated
+    assert combine.sam_lib_combine(tmp_path, holo.log, recreate=True, gwb_only=True).stem == "sam-library_gwb-only"
+    (sims / "library__p000004.npz").unlink()
+    with pytest.raises(ValueError):
+        combine.sam_lib_combine(tmp_path, holo.log, recreate=True)
