@@ -41,6 +41,13 @@ struct StageTimer {
 
 extern "C" int holo_check_launch(const char* who);
 
+namespace holo {
+// holo_realize.cu: realised GWB of a column slab of a wider grid (used by the eccentric harmonic sum)
+int realize_gwb_columns(const double* number, const double* h2fdf, int64_t ncell, int F, int R, int64_t r0,
+                        uint64_t seed, double normal_threshold, const double* counts, int key_col0, int key_cols,
+                        double* gwb, void* workspace, int64_t workspace_bytes, void* stream);
+}
+
 #define HOLO_REQUIRE(cond, msg)                      \
     do {                                             \
         if (!(cond)) {                               \

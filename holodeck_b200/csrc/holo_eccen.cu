@@ -86,90 +86,67 @@ ecc_sum_kernel(EccGeom g, EccConsts cc, const double* __restrict__ frst_pref, co
     if (threadIdx.x == 0) gwb[(int64_t)ff * g.H + (nh - 1)] = red[0];
 }
 
-// E3 (discrete): one CTA per (f, n, realization tile); threads = realizations.
-constexpr int ECC_TILE = 128;   // (z,M) pairs staged per pass
-
-__global__ void __launch_bounds__(ECC_THREADS)
-ecc_discrete_kernel(EccGeom g, EccConsts cc, const double* __restrict__ frst_pref, int R, int64_t r0,
-                    uint32_t k0, uint32_t k1, double* __restrict__ gwb /* (F,H,R) */) {
-    __shared__ double s_tau[ECC_TILE], s_h[ECC_TILE];
-    __shared__ int s_pair[ECC_TILE];
-    __shared__ int s_n;
-    const int fh = blockIdx.x;
-    const int ff = fh / g.H;
-    const int nh = fh % g.H + 1;
-    const int r = blockIdx.y * ECC_THREADS + threadIdx.x;
-    const bool live = r < R;
-    const int npair = g.Z * g.M;
+// E3 (discrete): gwb[f,n,r] = sum_cells Poisson(number_term) * hterm / weight  (pyx:783-839) is the realised-GWB
+// sum of the SAM path with (f,n) pairs as "frequencies": the (cell, column) expectation values and strain factors are
+// tabulated for a slab of columns and handed to the realization kernel (shared CDF tables, superposition groups).
+//   E3a  per (z,M,q):  c1 = ndens * 4 pi c d_c^2 (1+z) * volume / (m1 m2),  c2 = hterm_pref / weight
+//   E3b  per (z,M) x column: taufac, hfac (Bessel) once, then for all q:  number = c1 * taufac,  h = c2 * hfac
+__global__ void ecc_cell_consts_kernel(EccGeom g, EccConsts cc, double* __restrict__ c1, double* __restrict__ c2) {
+    const int64_t n = (int64_t)g.M * g.Q * g.Z;
     const double four_pi_c_mpc = 4 * CY_PI * (CY_SPLC / CY_MPC);
-    DrawKey key;
-    key.k0 = k0; key.k1 = k1; key.real = (uint32_t)(r0 + r); key.stream = 5;
-    double acc = 0.0;
-    for (int p0 = 0; p0 < npair; p0 += ECC_TILE) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_n = 0;
-        __syncthreads();
-        // stage the (z,M) pairs of this tile whose track covers (f,n): order within the tile is fixed by
-        // a serial compaction (thread 0), so the accumulation order is reproducible
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % g.Z);
+        const int64_t mq = i / g.Z;
+        const int jj = (int)(mq % g.Q), ii = (int)(mq / g.Q);
+        double kw, kdx, iw, idx_, jw, jdx;
+        trapz_grid_weight(kk, g.Z, g.redz, &kw, &kdx);
+        trapz_grid_weight(ii, g.M, g.mtot_log10, &iw, &idx_);
+        trapz_grid_weight(jj, g.Q, g.mrat, &jw, &jdx);
+        const double zterm = 1.0 + g.redz[kk];
+        const double dc_mpc = g.dcom[kk];
+        const double dc_cm = dc_mpc * CY_MPC;
+        const double dc_term = four_pi_c_mpc * pow(dc_mpc, 2.0);
+        const double mt = pow(10.0, g.mtot_log10[ii]);
+        const double volume = idx_ * kdx * jdx;                               // pyx:783-784
+        const double weight = iw * kw * jw;
+        const double q = g.mrat[jj];
+        const double m1 = mt / (1.0 + q);
+        const double m2 = mt - m1;
+        const double mchirp = mt * pow(q, 3.0 / 5.0) / pow(1 + q, 6.0 / 5.0);
+        const double nd = g.ndens[i];
+        const double number_term_pref = nd * dc_term * zterm;                 // pyx:799
+        const double hterm_pref = pow(cc.gw_src_const * mchirp * pow(2.0 * mchirp, 2.0 / 3.0) / dc_cm, 2.0);
+        c1[i] = (nd > 0.0) ? number_term_pref / (m1 * m2) * volume : 0.0;      // pyx:826, 829
+        c2[i] = hterm_pref / weight;                                          // pyx:832, 839
+    }
+}
+
+__global__ void __launch_bounds__(128)
+ecc_slab_kernel(EccGeom g, EccConsts cc, const double* __restrict__ frst_pref, const double* __restrict__ c1,
+                const double* __restrict__ c2, int col0, int ncol, double* __restrict__ number /* (ncell, ncol) */,
+                double* __restrict__ hval) {
+    const int p = blockIdx.x;                    // (z, M) pair
+    const int kk = p / g.M, ii = p % g.M;
+    for (int cl = threadIdx.x; cl < ncol; cl += blockDim.x) {
+        const int fh = col0 + cl;
         double afac, tf = 0.0, hf = 0.0;
-        bool ok = false;
-        const int p = p0 + threadIdx.x;
-        if (threadIdx.x < ECC_TILE && p < npair)
-            ok = eccen_factor(g, cc, frst_pref, p / g.M, p % g.M, ff, nh, &afac, &tf, &hf);
-        s_tau[threadIdx.x] = tf;
-        s_h[threadIdx.x] = hf;
-        s_pair[threadIdx.x] = ok ? p : -1;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int n = 0;
-            for (int i = 0; i < ECC_TILE; ++i) {
-                if (s_pair[i] >= 0) {
-                    const int pp = s_pair[i];
-                    const double a = s_tau[i], b = s_h[i];
-                    s_pair[n] = pp; s_tau[n] = a; s_h[n] = b;
-                    ++n;
-                }
-            }
-            s_n = n;
-        }
-        __syncthreads();
-        if (!live) continue;
-        for (int i = 0; i < s_n; ++i) {
-            const int pp = s_pair[i];
-            const int kk = pp / g.M, ii = pp % g.M;
-            double kw, kdx, iw, idx_;
-            trapz_grid_weight(kk, g.Z, g.redz, &kw, &kdx);
-            trapz_grid_weight(ii, g.M, g.mtot_log10, &iw, &idx_);
-            const double zterm = 1.0 + g.redz[kk];
-            const double dc_mpc = g.dcom[kk];
-            const double dc_cm = dc_mpc * CY_MPC;
-            const double dc_term = four_pi_c_mpc * pow(dc_mpc, 2.0);
-            const double mt = pow(10.0, g.mtot_log10[ii]);
-            const double volume_ik = idx_ * kdx;                             // pyx:783-784
-            const double weight_ik = iw * kw;
-            for (int jj = 0; jj < g.Q; ++jj) {
-                const double nd = g.ndens[((int64_t)ii * g.Q + jj) * g.Z + kk];
-                if (!(nd > 0.0)) continue;                                    // Poisson(0) = 0
-                double jw, jdx;
-                trapz_grid_weight(jj, g.Q, g.mrat, &jw, &jdx);
-                const double volume = volume_ik * jdx;
-                const double weight = weight_ik * jw;
-                const double q = g.mrat[jj];
-                const double m1 = mt / (1.0 + q);
-                const double m2 = mt - m1;
-                const double mchirp = mt * pow(q, 3.0 / 5.0) / pow(1 + q, 6.0 / 5.0);
-                const double number_term_pref = nd * dc_term * zterm;          // pyx:799
-                const double hterm_pref = pow(cc.gw_src_const * mchirp * pow(2.0 * mchirp, 2.0 / 3.0) / dc_cm, 2.0);
-                const double tau = s_tau[i] / (m1 * m2);                       // pyx:826
-                const double number_term = number_term_pref * tau * volume;    // pyx:829
-                const double hterm = hterm_pref * s_h[i];                      // pyx:832
-                const uint64_t idx = ((uint64_t)(((int64_t)ii * g.Q + jj) * g.Z + kk)) * (uint64_t)(g.F * g.H) + (uint64_t)fh;
-                const double num = draw_element(number_term, 1.0e300, key, idx);
-                acc += hterm * num / weight;                                   // pyx:839
-            }
+        const bool ok = (fh < g.F * g.H) && eccen_factor(g, cc, frst_pref, kk, ii, fh / g.H, fh % g.H + 1, &afac, &tf, &hf);
+        for (int jj = 0; jj < g.Q; ++jj) {
+            const int64_t cell = ((int64_t)ii * g.Q + jj) * g.Z + kk;
+            const double lam = ok ? c1[cell] * tf : 0.0;
+            number[cell * ncol + cl] = lam > 0.0 ? lam : 0.0;
+            hval[cell * ncol + cl] = ok ? c2[cell] * hf : 0.0;
         }
     }
-    if (live) gwb[(int64_t)fh * R + r] = acc;
+}
+
+static int ecc_slab_columns(int64_t ncell, int ncols_total) {
+    // columns per slab: a multiple of 4, two (ncell, cols) fp64 arrays within ~6 GB
+    int64_t cols = (int64_t)6.0e9 / (16 * ncell);
+    cols = (cols / 4) * 4;
+    if (cols < 4) cols = 4;
+    const int64_t all = ((int64_t)ncols_total + 3) / 4 * 4;
+    return (int)(cols < all ? cols : all);
 }
 
 }  // namespace holo
@@ -178,9 +155,18 @@ using namespace holo;
 
 extern "C" {
 
+int64_t holo_realize_workspace_bytes(int kind, int64_t ncell, int F, int R);
+
 int64_t holo_eccen_workspace_bytes(int M, int Q, int Z, int F, int nharms, int nreals) {
-    (void)Q; (void)F; (void)nharms; (void)nreals;
-    return 256 + 8 * ((int64_t)Z * M + 4096);
+    int64_t base = 256 + 8 * ((int64_t)Z * M + 4096);
+    if (nreals > 0) {
+        const int64_t ncell = (int64_t)M * Q * Z;
+        const int cols = ecc_slab_columns(ncell, F * nharms);
+        base += 2 * 8 * ncell + 256;                                   // c1, c2
+        base += 2 * 8 * ncell * cols + 512;                            // number, hval slabs
+        base += holo_realize_workspace_bytes(0, ncell, cols, nreals) + 256;
+    }
+    return base;
 }
 
 int holo_sam_calc_gwb_single_eccen(holo_cy_consts cyc, double gw_src_const, const double* ndens,
@@ -206,9 +192,37 @@ int holo_sam_calc_gwb_single_eccen(holo_cy_consts cyc, double gw_src_const, cons
         ecc_qsum_kernel<<<(Z * M + 127) / 128, 128, 0, st>>>(g, cc, bsum); holo::count_launches(1);
         ecc_sum_kernel<<<F * nharms, ECC_THREADS, 0, st>>>(g, cc, frst_pref, bsum, gwb); holo::count_launches(1);
     } else {
-        dim3 grid(F * nharms, (nreals + ECC_THREADS - 1) / ECC_THREADS);
-        ecc_discrete_kernel<<<grid, ECC_THREADS, 0, st>>>(g, cc, frst_pref, nreals, r0, (uint32_t)seed,
-                                                          (uint32_t)(seed >> 32), gwb); holo::count_launches(1);
+        const int64_t ncell = (int64_t)M * Q * Z;
+        const int FH = F * nharms;
+        const int cols = ecc_slab_columns(ncell, FH);
+        auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
+        unsigned char* wp = (unsigned char*)workspace + align(8 * ((int64_t)Z * M + 4096));
+        double* c1 = (double*)wp; wp += align(8 * ncell);
+        double* c2 = (double*)wp; wp += align(8 * ncell);
+        double* number = (double*)wp; wp += align(8 * ncell * cols);
+        double* hval = (double*)wp; wp += align(8 * ncell * cols);
+        const int64_t rws = (int64_t)((unsigned char*)workspace + workspace_bytes - wp);
+        ecc_cell_consts_kernel<<<148 * 8, 256, 0, st>>>(g, cc, c1, c2); holo::count_launches(1);
+        for (int col0 = 0; col0 < FH; col0 += cols) {
+            // the last slab keeps the full width (columns beyond F*H are empty) so that every slab is 4-aligned
+            ecc_slab_kernel<<<Z * M, 128, 0, st>>>(g, cc, frst_pref, c1, c2, col0, cols, number, hval); holo::count_launches(1);
+            int rc = holo_check_launch("holo_sam_calc_gwb_single_eccen: slab");
+            if (rc) return rc;
+            const int live = (FH - col0) < cols ? (FH - col0) : cols;
+            if (live == cols) {
+                rc = holo::realize_gwb_columns(number, hval, ncell, cols, nreals, r0, seed, 9.0e18, nullptr, col0, FH,
+                                               gwb + (int64_t)col0 * nreals, wp, rws, st);
+            } else {
+                // ragged tail: realise the full-width slab into scratch rows, copy the live rows out
+                double* tail = hval;   // reuse after the launch below has consumed it: stream-ordered
+                rc = holo::realize_gwb_columns(number, hval, ncell, cols, nreals, r0, seed, 9.0e18, nullptr, col0, FH,
+                                               number /* (cols, R) fits: cols*R <= ncell*cols */, wp, rws, st);
+                (void)tail;
+                if (!rc) HOLO_CUDA(cudaMemcpyAsync(gwb + (int64_t)col0 * nreals, number, sizeof(double) * (int64_t)live * nreals,
+                                                    cudaMemcpyDeviceToDevice, st));
+            }
+            if (rc) return rc;
+        }
     }
     return holo_check_launch("holo_sam_calc_gwb_single_eccen");
 }

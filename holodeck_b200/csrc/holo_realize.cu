@@ -86,6 +86,9 @@ struct RealizeArgs {
     int64_t r0;
     uint32_t k0, k1;
     double thresh;
+    // Philox counters use GLOBAL column indices so that a grid processed in column slabs (eccentric harmonics)
+    // draws independently in every slab: frequency group fg + fg_key0, element index cell*F_key + f + f_key0
+    int fg_key0, f_key0, F_key;
 };
 
 // One staged ELEMENT (cell, frequency slot) with a non-zero expectation value.
@@ -395,6 +398,7 @@ realize_kernel(RealizeArgs a) {
     const int fg = blockIdx.x;          // fastest: the CTAs sharing a chunk's 320 B rows run together (L2 reuse)
     const int chunk_id = blockIdx.y;
     const int f0 = fg * FGROUP;
+    const uint32_t fgk = (uint32_t)(fg + a.fg_key0);   // global frequency-group index (Philox counter)
     const int r_first = blockIdx.z * (blockDim.x * RPT) + tid;      // local realization of slot t = 0
     const int64_t c_lo = (int64_t)chunk_id * a.chunk;
     int64_t c_hi = c_lo + a.chunk;
@@ -491,7 +495,7 @@ realize_kernel(RealizeArgs a) {
 #pragma unroll
                     for (int u = 0; u < RPT; ++u) {
                         key.real = real_first + (uint32_t)u * blockDim.x;
-                        const Philox4 hi = group_bits(key, (uint32_t)rec.cell, (uint32_t)fg, PURPOSE_GROUP_HI);
+                        const Philox4 hi = group_bits(key, (uint32_t)rec.cell, fgk, PURPOSE_GROUP_HI);
                         s_words[0][u][tid] = hi.v[0]; s_words[1][u][tid] = hi.v[1];     // (thread-private columns:
                         s_words[2][u][tid] = hi.v[2]; s_words[3][u][tid] = hi.v[3];     //  no synchronisation needed)
                     }
@@ -511,7 +515,7 @@ realize_kernel(RealizeArgs a) {
                         if (table_ambiguous(s_pool, rec.toff, W, q[u], word[u])) {
                             key.real = real_first + (uint32_t)u * blockDim.x;
                             n[u] = table_resolve_keyed(rec.lam, s_pool + rec.toff, (int)rec.kmin, W, (int)(q[u] - rec.toff),
-                                                       word[u], key, (uint32_t)rec.cell, (uint32_t)fg, ord);
+                                                       word[u], key, (uint32_t)rec.cell, fgk, ord);
                         }
                     }
                     ++ord;
@@ -519,8 +523,8 @@ realize_kernel(RealizeArgs a) {
 #pragma unroll
                     for (int u = 0; u < RPT; ++u) {
                         key.real = real_first + (uint32_t)u * blockDim.x;
-                        n[u] = draw_normal_lam(rec.lam, key, (uint64_t)(uint32_t)rec.cell * (uint64_t)a.F +
-                                                             (uint64_t)(f0 + (int)(meta & 3u)));
+                        n[u] = draw_normal_lam(rec.lam, key, (uint64_t)(uint32_t)rec.cell * (uint64_t)a.F_key +
+                                                             (uint64_t)(a.f_key0 + f0 + (int)(meta & 3u)));
                     }
                 }
 #pragma unroll
@@ -555,7 +559,7 @@ realize_kernel(RealizeArgs a) {
                 //      process of rate Lambda = sum lam_k; each of its N events belongs to member k with
                 //      probability lam_k / Lambda (exact: superposition / thinning of Poisson processes)
                 if (ngrp > 0) {
-                    draw_group(s_pool, 1u, s_gspec[0], s_gspec[1], s_gspec[2], glam_tot, s_gcum, ngrp, pass_id, (uint32_t)fg,
+                    draw_group(s_pool, 1u, s_gspec[0], s_gspec[1], s_gspec[2], glam_tot, s_gcum, ngrp, pass_id, fgk,
                                key, [&](int member) {
                                    const int slot = NREC - 1 - member;
                                    const Rec rec = s_rec[slot];
@@ -572,7 +576,7 @@ realize_kernel(RealizeArgs a) {
                     const int i = s_plist[it];
                     const Rec rec = s_rec[i];
                     if (trial == 0) prep_draw(rec.lam, a.thresh, pp);
-                    const uint64_t idx = (uint64_t)(uint32_t)rec.cell * (uint64_t)a.F + (uint64_t)(f0 + (int)(rec.meta & 3u));
+                    const uint64_t idx = (uint64_t)(uint32_t)rec.cell * (uint64_t)a.F_key + (uint64_t)(a.f_key0 + f0 + (int)(rec.meta & 3u));
                     double k;
                     const bool ok = ptrs_trial(pp, element_bits(key, idx, trial), &k);
                     if (ok) {
@@ -1068,9 +1072,14 @@ int64_t holo_loudest_workspace_bytes(int variant, int64_t ncell, int F, int R, i
     return l.total;
 }
 
-int holo_sam_poisson_gwb(const double* number, const double* h2fdf, int64_t ncell, int F, int R,
-                         int64_t r0, uint64_t seed, double normal_threshold, const double* counts,
-                         double* gwb, void* workspace, int64_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+namespace holo {
+// sam_poisson_gwb on columns [key_col0, key_col0 + F) of a wider grid of `key_cols` columns (key_col0 % 4 == 0):
+// the Philox counters use the global column index, so slabs of one grid draw independently.
+int realize_gwb_columns(const double* number, const double* h2fdf, int64_t ncell, int F, int R, int64_t r0,
+                        uint64_t seed, double normal_threshold, const double* counts, int key_col0, int key_cols,
+                        double* gwb, void* workspace, int64_t workspace_bytes, void* stream) {
     HOLO_REQUIRE(number && h2fdf && gwb && workspace, "holo_sam_poisson_gwb: NULL argument");
     HOLO_REQUIRE(ncell > 0 && F > 0 && R > 0, "holo_sam_poisson_gwb: bad shape");
     HOLO_REQUIRE(ncell < 2147483647LL, "holo_sam_poisson_gwb: too many cells");
@@ -1083,6 +1092,7 @@ int holo_sam_poisson_gwb(const double* number, const double* h2fdf, int64_t ncel
     ra.ncell = ncell; ra.chunk = p.chunk; ra.Qb = 1; ra.Zb = 1; ra.F = F; ra.R = R; ra.cap = 0;
     ra.r0 = r0; ra.k0 = (uint32_t)seed; ra.k1 = (uint32_t)(seed >> 32);
     ra.thresh = (double)(int64_t)normal_threshold;                       // `long thresh`, pyx:855, 863
+    ra.fg_key0 = key_col0 / FGROUP; ra.f_key0 = key_col0; ra.F_key = key_cols > 0 ? key_cols : F;
     StageTimer timer(st);
     timer.mark();
     int rc = launch_realize<V_GWB>(ra, p, st);
@@ -1095,6 +1105,16 @@ int holo_sam_poisson_gwb(const double* number, const double* h2fdf, int64_t ncel
     timer.mark();
     timer.finish();
     return holo_check_launch("holo_sam_poisson_gwb");
+}
+}  // namespace holo
+
+extern "C" {
+
+int holo_sam_poisson_gwb(const double* number, const double* h2fdf, int64_t ncell, int F, int R,
+                         int64_t r0, uint64_t seed, double normal_threshold, const double* counts,
+                         double* gwb, void* workspace, int64_t workspace_bytes, void* stream) {
+    return holo::realize_gwb_columns(number, h2fdf, ncell, F, R, r0, seed, normal_threshold, counts, 0, 0, gwb, workspace,
+                                     workspace_bytes, stream);
 }
 
 int holo_loudest(const holo_loudest_args* g, void* stream) {
@@ -1153,6 +1173,7 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     ra.ncell = ncell; ra.chunk = p.chunk; ra.Qb = g->Qb; ra.Zb = g->Zb; ra.F = F; ra.R = R; ra.cap = cap;
     ra.r0 = g->r0; ra.k0 = (uint32_t)g->seed; ra.k1 = (uint32_t)(g->seed >> 32);
     ra.thresh = (double)(int64_t)g->normal_threshold;
+    ra.fg_key0 = 0; ra.f_key0 = 0; ra.F_key = F;
     if (v == V_LOUD_PLAIN) rc = launch_realize<V_LOUD_PLAIN>(ra, p, st);
     else if (v == V_LOUD_PAR) rc = launch_realize<V_LOUD_PAR>(ra, p, st);
     else rc = launch_realize<V_LOUD_PAR_REDZ>(ra, p, st);
@@ -1229,6 +1250,7 @@ int holo_ss_bg_hc(const double* number, const double* h2fdf, int Mb, int Qb, int
     ra.ncell = ncell; ra.chunk = p.chunk; ra.Qb = Qb; ra.Zb = Zb; ra.F = F; ra.R = R;
     ra.r0 = r0; ra.k0 = (uint32_t)seed; ra.k1 = (uint32_t)(seed >> 32);
     ra.thresh = (double)(int64_t)normal_threshold;
+    ra.fg_key0 = 0; ra.f_key0 = 0; ra.F_key = F;
     int rc = par ? launch_realize<V_SSBG_PAR>(ra, p, st) : launch_realize<V_SSBG>(ra, p, st);
     if (rc) return rc;
     FinalArgs fa{};

@@ -40,7 +40,11 @@ print("config0  default SAM(30) Hard_GW R=10  %.2f ms" % timeit(lambda: holo.sam
 sam, hard = bench.make_models(args)
 sepa, ecc = holo.sams.evolve_eccen_uniform_single(sam, 0.9, 10*PC, 123)
 print("config4  eccentric continuous 91x81x101, F=40, H=100  %.1f ms" % timeit(lambda: holo.gravwaves.sam_calc_gwb_single_eccen(fobs_cents, sam, sepa, ecc, nharms=100)))
-t0 = time.perf_counter()
-out = holo.gravwaves.sam_calc_gwb_single_eccen_discrete(fobs_cents[:4], sam, sepa, ecc, nharms=10, nreals=500, seed=1)
-torch.cuda.synchronize()
-print("config4' eccentric discrete, F=4, H=10, R=500 (1/100 of the (f,n) grid)  %.1f ms" % ((time.perf_counter() - t0) * 1e3), out.shape)
+for rep in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    out = holo.gravwaves.sam_calc_gwb_single_eccen_discrete(fobs_cents, sam, sepa, ecc, nharms=100, nreals=500, seed=1)
+    torch.cuda.synchronize()
+    print("config4' eccentric discrete, F=40, H=100, R=500 (full grid)  %.1f ms" % ((time.perf_counter() - t0) * 1e3), tuple(out.shape))
+cont = holo.gravwaves.sam_calc_gwb_single_eccen(fobs_cents, sam, sepa, ecc, nharms=100)
+mean = out.mean(axis=2)
+print("   mean over realizations / continuous (sum over harmonics, first 5 freqs):", (mean.sum(axis=1) / cont.sum(axis=1))[:5])
