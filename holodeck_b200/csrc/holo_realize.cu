@@ -967,16 +967,15 @@ struct Plan {
 
 static Plan make_plan(int64_t ncell, int F, int R, int variant) {
     Plan p;
-    const int nacc = nacc_of(variant), rpt = rpt_of(variant);
+    const int rpt = rpt_of(variant);
     p.threads = RZ_THREADS;   // always: the staging scan is one thread per cell of a 256-cell window (see stage_pass)
     p.ntiles = (R + p.threads * rpt - 1) / (p.threads * rpt);
     p.nfg = (F + FGROUP - 1) / FGROUP;
     // The cell chunking must not depend on R (or on the realization tiling): per-chunk partial sums are
     // combined in a fixed order, so a fixed chunking makes hc2 bit-identical however the realizations
-    // are partitioned over launches / GPUs.  It only depends on the number of accumulators per thread
-    // (partials cost nchunk*F*NACC*R*8 bytes); 512 chunks x (F/4) CTAs keep 148 SMs busy even when one
-    // CTA carries all realizations.
-    int64_t nchunk = nacc >= 8 ? 128 : (nacc >= 4 ? 256 : 512);
+    // are partitioned over launches / GPUs (partials cost nchunk*F*NACC*R*8 bytes: 164 MB ... 1.3 GB at R = 1000);
+    // 512 chunks x (F/4) CTAs keep 148 SMs busy even when one CTA carries all realizations.
+    int64_t nchunk = 512;
     int64_t chunk = (ncell + nchunk - 1) / nchunk;
     chunk = ((chunk + 63) / 64) * 64;
     if (chunk < 64) chunk = 64;
