@@ -232,6 +232,8 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import holodeck_b200 as holo   # noqa: F401
     from holodeck_b200 import _lib, utils
