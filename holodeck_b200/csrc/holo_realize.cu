@@ -201,6 +201,21 @@ __device__ __forceinline__ void fold_rec(const RealizeArgs& a, const Rec& rec, c
     }
 }
 
+// Accumulators in shared memory (variants with one sum per frequency and no running maximum): the frequency slot
+// is a run-time index, so the fold is load / fma / store on a thread-private column -- no four-way dispatch, and
+// sixteen registers fewer in the draw loops.  `col` = &s_acc[0][u][tid]; consecutive frequency slots are
+// SACC_STRIDE doubles apart.
+template <int VARIANT>
+__device__ __forceinline__ void fold_sacc(const RealizeArgs& a, const Rec& rec, int f0, int r, double n, double* col,
+                                          int stride) {
+    const int fi = (int)(rec.meta & 3u);
+    if (has_events(VARIANT) && (rec.meta & META_HEAD)) {
+        if (n >= 1.0) push_event(a, f0 + fi, r, rec.cell, n);           // pyx:1333-1341
+    } else {
+        col[fi * stride] += n * rec.h;                                  // pyx:891-895, 1342
+    }
+}
+
 // One warp tabulates the CDF of Poisson(lam) over its window as 32-bit thresholds (see holo_rng.cuh);
 // t[-1] = 0 and t[W] = 2^32-1 are sentinels for the ambiguity test of the draw.
 static __device__ __noinline__ void build_table_warp(double lam, uint32_t* t, int kmin, int W, int lane) {
@@ -407,6 +422,15 @@ realize_kernel(RealizeArgs a) {
     const bool supplied = a.counts != nullptr;
     const bool vec4 = (nf == FGROUP) && ((a.F & 3) == 0);   // 32 B-aligned frequency groups
 
+    constexpr bool SACC = (NACC == 1) && !has_max(VARIANT);       // accumulators in shared memory (see fold_sacc)
+    constexpr int SACC_STRIDE = RPT * RZ_THREADS;
+    __shared__ double s_acc[SACC ? FGROUP : 1][SACC ? RPT : 1][SACC ? RZ_THREADS : 1];
+    if (SACC) {
+#pragma unroll
+        for (int fi = 0; fi < FGROUP; ++fi)
+#pragma unroll
+            for (int t = 0; t < RPT; ++t) s_acc[SACC ? fi : 0][SACC ? t : 0][SACC ? tid : 0] = 0.0;
+    }
     double acc[RPT][FGROUP][NACC];
     double vmax[RPT][FGROUP];
     int imax[RPT][FGROUP];
@@ -476,7 +500,8 @@ realize_kernel(RealizeArgs a) {
                     const int r = r_first + u * (int)blockDim.x;
                     if (r >= a.R) continue;
                     const double n = a.counts[((int64_t)r * a.F + f) * a.ncell + rec.cell];
-                    fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, n, acc[u], vmax[u], imax[u]);
+                    if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, n, &s_acc[0][SACC ? u : 0][SACC ? tid : 0], SACC_STRIDE);
+                    else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, n, acc[u], vmax[u], imax[u]);
                 }
             }
             continue;
@@ -531,7 +556,8 @@ realize_kernel(RealizeArgs a) {
                 for (int u = 0; u < RPT; ++u) {
                     const int r = r_first + u * (int)blockDim.x;
                     if (r >= a.R) continue;
-                    fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, n[u], acc[u], vmax[u], imax[u]);
+                    if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, n[u], &s_acc[0][SACC ? u : 0][SACC ? tid : 0], SACC_STRIDE);
+                    else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, n[u], acc[u], vmax[u], imax[u]);
                 }
             }
         }
@@ -563,8 +589,9 @@ realize_kernel(RealizeArgs a) {
                                key, [&](int member) {
                                    const int slot = NREC - 1 - member;
                                    const Rec rec = s_rec[slot];
-                                   fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? slot : 0], s_w4[NACC > 4 ? slot : 0], f0, r, 1.0,
-                                                     tacc, tvmax, timax);
+                                   if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, 1.0, &s_acc[0][0][SACC ? tid : 0] + u * RZ_THREADS, SACC_STRIDE);
+                                   else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? slot : 0], s_w4[NACC > 4 ? slot : 0], f0, r, 1.0,
+                                                          tacc, tvmax, timax);
                                });
                 }
                 // ---- phase B, lane-decoupled: each lane walks the PTRS list at its own pace (one rejection trial
@@ -580,7 +607,8 @@ realize_kernel(RealizeArgs a) {
                     double k;
                     const bool ok = ptrs_trial(pp, element_bits(key, idx, trial), &k);
                     if (ok) {
-                        fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, k, tacc, tvmax, timax);
+                        if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, k, &s_acc[0][0][SACC ? tid : 0] + u * RZ_THREADS, SACC_STRIDE);
+                        else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, k, tacc, tvmax, timax);
                         ++it;
                         trial = 0;
                     } else {
@@ -589,7 +617,7 @@ realize_kernel(RealizeArgs a) {
                 }
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
-                    if (j == u) {
+                    if (!SACC && j == u) {
 #pragma unroll
                         for (int fi = 0; fi < FGROUP; ++fi) {
 #pragma unroll
@@ -616,7 +644,8 @@ realize_kernel(RealizeArgs a) {
             const int f = f0 + fi;
             int64_t pb = ((int64_t)chunk_id * a.F + f) * NACC;
 #pragma unroll
-            for (int k = 0; k < NACC; ++k) a.partial[(pb + k) * a.R + r] = acc[t][fi][k];
+            for (int k = 0; k < NACC; ++k)
+                a.partial[(pb + k) * a.R + r] = SACC ? s_acc[SACC ? fi : 0][SACC ? t : 0][SACC ? tid : 0] : acc[t][fi][k];
             if (has_max(VARIANT)) {
                 int64_t mb = ((int64_t)chunk_id * a.F + f) * a.R + r;
                 a.pmax[mb] = vmax[t][fi];
