@@ -46,7 +46,7 @@ __host__ __device__ constexpr bool has_events(int v) {
 }
 __host__ __device__ constexpr bool has_max(int v) { return v == V_SSBG || v == V_SSBG_PAR; }
 
-constexpr int RZ_THREADS = 256;      // threads per CTA (max); each thread carries rpt_of(VARIANT) realizations
+constexpr int RZ_THREADS = 256;      // threads per CTA; each thread carries RPT realization slots (see rpt_for)
 constexpr int NSCAN = 256;           // cells scanned per pass (max) = threads per CTA
 constexpr int FGROUP = 4;            // frequencies per CTA (4 doubles = one 32 B sector per cell)
 constexpr int POOL_ENTRIES = 6144;   // 32-bit CDF thresholds per pass (24 KB of dynamic shared memory)
@@ -108,17 +108,18 @@ __host__ __device__ constexpr int nrec_of(int nacc) { return nacc == 1 ? 512 : 2
 
 // realizations carried by one thread: the per-CTA work that does not depend on the realization (staging,
 // CDF tables) is shared by blockDim * rpt realizations; bounded by the accumulator registers
-#ifndef HOLO_RPT_MAIN
-#define HOLO_RPT_MAIN 2
-#endif
-#ifndef HOLO_MINB_MAIN
-#define HOLO_MINB_MAIN 3
-#endif
-__host__ __device__ constexpr int rpt_of(int variant) {
-    return (variant == V_GWB || variant == V_LOUD_PLAIN) ? HOLO_RPT_MAIN : (variant == V_SSBG ? 2 : 1);
+// The two main variants (realised GWB, loudest split without parameters) pick the number of lock-step slots from
+// the realization count: 4 slots (one CTA then carries 1024 realizations: a single staging pass at R = 1000),
+// 2 or 1 for small R so that no slot is dead.  Results do not depend on the choice (draws are keyed on the
+// global realization index, pass boundaries on the cells only).
+__host__ __device__ constexpr bool flexible_rpt(int variant) { return variant == V_GWB || variant == V_LOUD_PLAIN; }
+__host__ __device__ constexpr int rpt_of(int variant) { return variant == V_SSBG ? 2 : 1; }       // fixed-slot variants
+inline int rpt_for(int variant, int R) {
+    if (!flexible_rpt(variant)) return rpt_of(variant);
+    return R > 2 * RZ_THREADS ? 4 : (R > RZ_THREADS ? 2 : 1);
 }
-__host__ __device__ constexpr int min_ctas_of(int variant) {
-    return (variant == V_GWB || variant == V_LOUD_PLAIN) ? HOLO_MINB_MAIN : 2;
+__host__ __device__ constexpr int min_ctas_of(int variant, int rpt) {
+    return flexible_rpt(variant) ? (rpt >= 4 ? 2 : 3) : 2;
 }
 
 // The FGROUP consecutive frequencies of one cell are one aligned 32 B sector when F % 4 == 0: read them
@@ -388,11 +389,10 @@ static __device__ __forceinline__ int stage_pass(const RealizeArgs& a, int64_t c
     return ncons;
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(RZ_THREADS, min_ctas_of(VARIANT))
+template <int VARIANT, int RPT>
+__global__ void __launch_bounds__(RZ_THREADS, min_ctas_of(VARIANT, RPT))
 realize_kernel(RealizeArgs a) {
     constexpr int NACC = nacc_of(VARIANT);
-    constexpr int RPT = rpt_of(VARIANT);
     constexpr int NREC = nrec_of(NACC);
     __shared__ __align__(16) Rec s_rec[NREC];           // main records grow from 0, group records from NREC-1 down
     __shared__ double s_w3[NACC > 1 ? NREC : 1][3];     // mt, mr, rz of the record's cell (parameter variants)
@@ -405,8 +405,7 @@ realize_kernel(RealizeArgs a) {
     __shared__ double s_totlam;
     __shared__ int s_np;
     __shared__ int s_gspec[3];                          // kmin, W, lg of the group's table
-    __shared__ uint32_t s_words[4][RPT][RZ_THREADS];    // each thread's Philox block of the current cell, per slot
-    extern __shared__ uint32_t s_pool[];                // POOL_ENTRIES thresholds
+    extern __shared__ __align__(16) uint32_t s_pool[];  // POOL_ENTRIES thresholds, then s_acc / s_words (below)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarp = blockDim.x >> 5;
@@ -424,7 +423,12 @@ realize_kernel(RealizeArgs a) {
 
     constexpr bool SACC = (NACC == 1) && !has_max(VARIANT);       // accumulators in shared memory (see fold_sacc)
     constexpr int SACC_STRIDE = RPT * RZ_THREADS;
-    __shared__ double s_acc[SACC ? FGROUP : 1][SACC ? RPT : 1][SACC ? RZ_THREADS : 1];
+    // dynamic shared memory: [pool | accumulators (SACC) | each thread's Philox block of the current cell, per slot]
+    typedef double AccArr[SACC ? RPT : 1][SACC ? RZ_THREADS : 1];
+    typedef uint32_t WordArr[RPT][RZ_THREADS];
+    AccArr* s_acc = reinterpret_cast<AccArr*>(s_pool + POOL_ENTRIES);                       // [FGROUP][RPT][RZ_THREADS]
+    WordArr* s_words = reinterpret_cast<WordArr*>(reinterpret_cast<double*>(s_pool + POOL_ENTRIES) +
+                                                  (SACC ? FGROUP * RPT * RZ_THREADS : 0));   // [4][RPT][RZ_THREADS]
     if (SACC) {
 #pragma unroll
         for (int fi = 0; fi < FGROUP; ++fi)
@@ -990,13 +994,14 @@ bulk_poisson_kernel(const double* __restrict__ lam, int64_t n, uint32_t k0, uint
 // host-side planning
 // -------------------------------------------------------------------------------------------------
 struct Plan {
-    int threads, ntiles, nfg, nchunk;
+    int threads, ntiles, nfg, nchunk, rpt;
     int64_t chunk;
 };
 
 static Plan make_plan(int64_t ncell, int F, int R, int variant) {
     Plan p;
-    const int rpt = rpt_of(variant);
+    const int rpt = rpt_for(variant, R);
+    p.rpt = rpt;
     p.threads = RZ_THREADS;   // always: the staging scan is one thread per cell of a 256-cell window (see stage_pass)
     p.ntiles = (R + p.threads * rpt - 1) / (p.threads * rpt);
     p.nfg = (F + FGROUP - 1) / FGROUP;
@@ -1064,18 +1069,29 @@ static Layout carve(void* ws, int variant, int64_t ncell, int F, int R, int cap,
     return l;
 }
 
-template <int VARIANT>
-static int launch_realize(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
+template <int VARIANT, int RPT>
+static int launch_realize_rpt(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
     dim3 grid(p.nfg, p.nchunk, p.ntiles);
-    const size_t pool_bytes = sizeof(uint32_t) * POOL_ENTRIES;
+    const bool sacc = nacc_of(VARIANT) == 1 && !has_max(VARIANT);
+    const size_t pool_bytes = sizeof(uint32_t) * POOL_ENTRIES + (sacc ? sizeof(double) * FGROUP * RPT * RZ_THREADS : 0) +
+                              sizeof(uint32_t) * 4 * RPT * RZ_THREADS;
     static bool attr_set = false;   // static + dynamic shared memory may exceed the 48 KB default
     if (!attr_set) {
-        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
-        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
+        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
-    realize_kernel<VARIANT><<<grid, p.threads, pool_bytes, st>>>(ra); holo::count_launches(1);
+    realize_kernel<VARIANT, RPT><<<grid, p.threads, pool_bytes, st>>>(ra); holo::count_launches(1);
     return holo_check_launch("realize_kernel");
+}
+
+template <int VARIANT>
+static int launch_realize(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
+    if (flexible_rpt(VARIANT)) {
+        if (p.rpt == 4) return launch_realize_rpt<VARIANT, flexible_rpt(VARIANT) ? 4 : rpt_of(VARIANT)>(ra, p, st);
+        if (p.rpt == 2) return launch_realize_rpt<VARIANT, flexible_rpt(VARIANT) ? 2 : rpt_of(VARIANT)>(ra, p, st);
+    }
+    return launch_realize_rpt<VARIANT, rpt_of(VARIANT)>(ra, p, st);
 }
 
 }  // namespace holo
