@@ -49,7 +49,10 @@ __host__ __device__ constexpr bool has_max(int v) { return v == V_SSBG || v == V
 constexpr int RZ_THREADS = 256;      // threads per CTA; each thread carries RPT realization slots (see rpt_for)
 constexpr int NSCAN = 256;           // cells scanned per pass (max) = threads per CTA
 constexpr int FGROUP = 4;            // frequencies per CTA (4 doubles = one 32 B sector per cell)
-constexpr int POOL_ENTRIES = 6144;   // 32-bit CDF thresholds per pass (24 KB of dynamic shared memory)
+#ifndef HOLO_POOL_ENTRIES
+#define HOLO_POOL_ENTRIES 6144
+#endif
+constexpr int POOL_ENTRIES = HOLO_POOL_ENTRIES;   // 32-bit CDF thresholds per pass (24 KB of dynamic shared memory)
 constexpr int GROUP_RESERVE = 288;   // head of the pool: CDF table of the pass's superposition group
 constexpr double GROUP_MAX_LAM = 0.25;   // elements below this expectation value are drawn as one Poisson process
 constexpr int CLS_GROUP = 6;         // (continues the CLS_* enum of holo_rng.cuh) member of the superposition group
@@ -698,18 +701,40 @@ head_sum_kernel(const double* __restrict__ number, const double* __restrict__ h2
     for (int f = threadIdx.x; f < F; f += blockDim.x) bsum[(int64_t)blockIdx.x * F + f] = s_sum[f];
 }
 
+// One warp per frequency: lanes sum contiguous segments of the per-block occupancy sums, a warp scan locates the
+// segment in which the cumulative sum crosses `target`, and that lane walks its segment (fixed order).
 __global__ void head_cut_kernel(const double* __restrict__ bsum, int nblk, int F, int64_t ncell,
                                 double target, int32_t* __restrict__ kf) {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (f >= F) return;
-    double cum = 0.0;
-    int64_t k = ncell;
-    for (int b = 0; b < nblk; ++b) {
-        cum += bsum[(int64_t)b * F + f];
-        if (cum >= target) { k = (int64_t)(b + 1) * HEAD_ROWS; break; }
+    const int seg = (nblk + 31) / 32;
+    const int b0 = lane * seg, b1 = min(nblk, b0 + seg);
+    double mine = 0.0;
+    for (int b = b0; b < b1; ++b) mine += bsum[(int64_t)b * F + f];
+    double incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
     }
-    if (k > ncell) k = ncell;
-    kf[f] = (int32_t)k;
+    const bool crosses = (incl >= target) && (incl - mine < target);
+    const unsigned who = __ballot_sync(0xffffffffu, crosses);
+    int64_t k = ncell;
+    if (who != 0u) {
+        const int owner = __ffs(who) - 1;
+        if (lane == owner) {
+            double cum = incl - mine;
+            for (int b = b0; b < b1; ++b) {
+                cum += bsum[(int64_t)b * F + f];
+                if (cum >= target) { k = (int64_t)(b + 1) * HEAD_ROWS; break; }
+            }
+            if (k > ncell) k = ncell;
+            kf[f] = (int32_t)k;
+        }
+    } else if (lane == 0) {
+        kf[f] = (int32_t)ncell;
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1203,7 +1228,7 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     head_sum_kernel<<<nblk, 256, sizeof(double) * F, st>>>(
         g->number, g->h2fdf, g->order, ncell, F, (double)(int64_t)g->normal_threshold,
         v == V_LOUD_PAR_REDZ ? 1 : 0, g->counts ? 1 : 0, l.bsum); holo::count_launches(1);
-    head_cut_kernel<<<(F + 63) / 64, 64, 0, st>>>(l.bsum, nblk, F, ncell, (double)L + margin, l.kf); holo::count_launches(1);
+    head_cut_kernel<<<(F + 3) / 4, 128, 0, st>>>(l.bsum, nblk, F, ncell, (double)L + margin, l.kf); holo::count_launches(1);
     int rc = holo_check_launch("holo_loudest: head preparation");
     if (rc) return rc;
 
