@@ -289,6 +289,10 @@ HOLO_HD bool dbn_2pwl_cell_from(const CyConsts& cc, const MqConsts& mq, const Tr
         *redz_out = new_redz;
         *dnum_out = nden * tres * cosmo_fact;                          // pyx:768
         found = true;
+        // The next step can only bracket the target too if its left edge -- the same point of the track as this
+        // step's right edge, recomputed: equal to a few ulp -- is <= ftarget, i.e. at an exact tie.  1e-12 is
+        // three orders of magnitude above the rounding of that recomputation, so nothing is skipped wrongly.
+        if (ftarget < fobs_right * (1.0 - 1.0e-12)) break;
     }
     return found;
 }

@@ -194,3 +194,10 @@ def test_realizations_do_not_depend_on_partition(holo, golden_classic):
     g2 = np.concatenate([cyutils.sam_poisson_gwb(gg["number"], gg["h2fdf"], 4, seed=7, r0=rr) for rr in (0, 4)], axis=1)
     assert np.array_equal(g1, g2)
     assert not np.array_equal(g1, cyutils.sam_poisson_gwb(gg["number"], gg["h2fdf"], 8, seed=8))
+    # ... and across the lock-step slot counts the kernel picks from R (600 -> 4 slots, 300 -> 2, 150 -> 1)
+    big = cyutils.loudest_hc_from_sorted(gg["number"], gg["h2fdf"], 600, 2, ms, qs, zs, seed=9)
+    halves = [cyutils.loudest_hc_from_sorted(gg["number"], gg["h2fdf"], 300, 2, ms, qs, zs, seed=9, r0=rr) for rr in (0, 300)]
+    quarters = [cyutils.sam_poisson_gwb(gg["number"], gg["h2fdf"], 150, seed=9, r0=rr) for rr in (0, 150, 300, 450)]
+    assert np.array_equal(big[0], np.concatenate([hh[0] for hh in halves], axis=1))
+    assert np.array_equal(big[1], np.concatenate([hh[1] for hh in halves], axis=1))
+    assert np.array_equal(cyutils.sam_poisson_gwb(gg["number"], gg["h2fdf"], 600, seed=9), np.concatenate(quarters, axis=1))
