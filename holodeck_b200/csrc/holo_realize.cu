@@ -46,8 +46,8 @@ __host__ __device__ constexpr bool has_events(int v) {
 }
 __host__ __device__ constexpr bool has_max(int v) { return v == V_SSBG || v == V_SSBG_PAR; }
 
-constexpr int RZ_THREADS = 256;      // threads per CTA; each thread carries RPT realization slots (see rpt_for)
-constexpr int NSCAN = 256;           // cells scanned per pass (max) = threads per CTA
+constexpr int RZ_THREADS = 256;      // threads per CTA (128 when R <= 128); each thread carries RPT realization slots
+constexpr int NSCAN = 256;           // cells scanned per pass (max), in rounds of one cell per thread
 constexpr int FGROUP = 4;            // frequencies per CTA (4 doubles = one 32 B sector per cell)
 #ifndef HOLO_POOL_ENTRIES
 #define HOLO_POOL_ENTRIES 6144
@@ -58,6 +58,22 @@ constexpr double GROUP_MAX_LAM = 0.25;   // elements below this expectation valu
 constexpr int CLS_GROUP = 6;         // (continues the CLS_* enum of holo_rng.cuh) member of the superposition group
 constexpr int STREAM_GWB = 1, STREAM_LOUD = 2, STREAM_SSBG = 3, STREAM_BULK = 4;
 static_assert(FGROUP * (TABLE_WMAX + 2) + GROUP_RESERVE <= POOL_ENTRIES, "one cell must always fit the table pool");
+
+// Debug instrumentation (never in the product build): -DHOLO_PHASE_CLOCKS makes thread 0 of every CTA add the
+// clock64 cycles it spends in each phase of a pass to g_phase_clk (read with holo_debug_phase_clocks).
+#ifdef HOLO_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[8];
+#define HOLO_PHASE_DECL long long ph_last = clock64();
+#define HOLO_PHASE_MARK(i)                                                          \
+    if (threadIdx.x == 0) {                                                         \
+        const long long ph_now = clock64();                                         \
+        atomicAdd(&g_phase_clk[i], (unsigned long long)(ph_now - ph_last));         \
+        ph_last = ph_now;                                                           \
+    }
+#else
+#define HOLO_PHASE_DECL
+#define HOLO_PHASE_MARK(i)
+#endif
 
 struct Event {
     int rank;
@@ -121,9 +137,13 @@ inline int rpt_for(int variant, int R) {
     if (!flexible_rpt(variant)) return rpt_of(variant);
     return R > 2 * RZ_THREADS ? 4 : (R > RZ_THREADS ? 2 : 1);
 }
-__host__ __device__ constexpr int min_ctas_of(int variant, int rpt) {
-    return flexible_rpt(variant) ? (rpt >= 4 ? 2 : 3) : 2;
+__host__ __device__ constexpr int min_ctas_of(int variant, int rpt, int threads) {
+    return threads <= 128 ? 4 : (flexible_rpt(variant) ? (rpt >= 4 ? 2 : 3) : 2);
 }
+// Small realization counts run 128-thread CTAs (four per SM instead of two): the work per pass that does not depend
+// on R is a chain of dependent latencies, so more resident CTAs is what hides it.  The staging scan then takes the
+// 256-cell window in two rounds; pass boundaries, records and tables are the same as with 256 threads.
+inline int threads_for(int rpt, int R) { return (rpt == 1 && R <= 128) ? 128 : RZ_THREADS; }
 
 // The FGROUP consecutive frequencies of one cell are one aligned 32 B sector when F % 4 == 0: read them
 // with two 16 B loads instead of four strided 8 B loads.
@@ -246,25 +266,31 @@ static __device__ __noinline__ void build_table_warp(double lam, uint32_t* t, in
 // Stage the next run of cells of a pass (see the kernel): thread <-> cell, elements compacted in (cell, frequency)
 // order into `s_rec` (main records from 0 up, group members from NREC-1 down).  Returns the number of cells
 // consumed; *s_tot / *s_totlam receive the packed record counts and the group's total expectation value.
-// The CTA always has NSCAN threads (idle in the draw loops when R is small), so the pass boundaries -- and with
-// them the membership of the superposition groups -- never depend on how the realizations are tiled.
-template <int VARIANT>
+// The window is always NSCAN cells and the record / pool limits are fixed, so the pass boundaries -- and with
+// them the membership of the superposition groups -- never depend on how the realizations are tiled or on the
+// CTA size (the scans carry over from one round of THREADS cells to the next in cell order).
+template <int VARIANT, int THREADS>
 static __device__ __forceinline__ int stage_pass(const RealizeArgs& a, int64_t cb, int64_t c_hi, int f0, int nf, Rec* s_rec,
                                               double* s_w3, double* s_w4, double* s_gcum, unsigned long long* s_wsum,
-                                              double* s_wlam, unsigned long long* s_tot, double* s_totlam) {
+                                              double* s_wlam, unsigned long long* s_tot, double* s_totlam
+#ifdef HOLO_PHASE_CLOCKS
+                                              , long long& ph_last
+#endif
+                                              ) {
     constexpr int NACC = nacc_of(VARIANT);
     constexpr int NREC = nrec_of(NACC);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int nwarp = NSCAN / 32;
+    constexpr int nwarp = THREADS / 32;
     const bool supplied = a.counts != nullptr;
     const bool vec4 = (nf == FGROUP) && ((a.F & 3) == 0);   // 32 B-aligned frequency groups
     __syncthreads();   // previous pass fully consumed
+    HOLO_PHASE_MARK(4)   // waiting for the slowest thread of the previous pass
     int ncons = 0;
     unsigned long long carry = 0;
     double carry_lam = 0.0;
-    for (int sbase = 0; sbase < NSCAN; sbase += NSCAN) {      // (a single round: blockDim.x == NSCAN)
+    for (int sbase = 0; sbase < NSCAN; sbase += THREADS) {    // one or two rounds of THREADS cells
         const int64_t c = cb + sbase + tid;
-        const bool inrange = (c < c_hi) && (sbase + tid < NSCAN);
+        const bool inrange = (c < c_hi);
         unsigned clsw = 0;            // CLS_* byte per frequency slot
         unsigned nmain_t = 0, ngrp_t = 0, need_t = 0;
         double glam_t = 0.0;
@@ -387,13 +413,13 @@ static __device__ __forceinline__ int stage_pass(const RealizeArgs& a, int64_t c
         ncons += ntaken;
         carry = round_tot;
         carry_lam = round_lam;
-        if (ntaken < NSCAN) break;
+        if (ntaken < THREADS) break;
     }
     return ncons;
 }
 
-template <int VARIANT, int RPT>
-__global__ void __launch_bounds__(RZ_THREADS, min_ctas_of(VARIANT, RPT))
+template <int VARIANT, int RPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, min_ctas_of(VARIANT, RPT, THREADS))
 realize_kernel(RealizeArgs a) {
     constexpr int NACC = nacc_of(VARIANT);
     constexpr int NREC = nrec_of(NACC);
@@ -425,13 +451,13 @@ realize_kernel(RealizeArgs a) {
     const bool vec4 = (nf == FGROUP) && ((a.F & 3) == 0);   // 32 B-aligned frequency groups
 
     constexpr bool SACC = (NACC == 1) && !has_max(VARIANT);       // accumulators in shared memory (see fold_sacc)
-    constexpr int SACC_STRIDE = RPT * RZ_THREADS;
+    constexpr int SACC_STRIDE = RPT * THREADS;
     // dynamic shared memory: [pool | accumulators (SACC) | each thread's Philox block of the current cell, per slot]
-    typedef double AccArr[SACC ? RPT : 1][SACC ? RZ_THREADS : 1];
-    typedef uint32_t WordArr[RPT][RZ_THREADS];
-    AccArr* s_acc = reinterpret_cast<AccArr*>(s_pool + POOL_ENTRIES);                       // [FGROUP][RPT][RZ_THREADS]
+    typedef double AccArr[SACC ? RPT : 1][SACC ? THREADS : 1];
+    typedef uint32_t WordArr[RPT][THREADS];
+    AccArr* s_acc = reinterpret_cast<AccArr*>(s_pool + POOL_ENTRIES);                       // [FGROUP][RPT][THREADS]
     WordArr* s_words = reinterpret_cast<WordArr*>(reinterpret_cast<double*>(s_pool + POOL_ENTRIES) +
-                                                  (SACC ? FGROUP * RPT * RZ_THREADS : 0));   // [4][RPT][RZ_THREADS]
+                                                  (SACC ? FGROUP * RPT * THREADS : 0));      // [4][RPT][THREADS]
     if (SACC) {
 #pragma unroll
         for (int fi = 0; fi < FGROUP; ++fi)
@@ -459,14 +485,20 @@ realize_kernel(RealizeArgs a) {
     const uint32_t real_first = (uint32_t)(a.r0 + r_first);
 
     int64_t cb = c_lo;
+    HOLO_PHASE_DECL
     while (cb < c_hi) {
         // ---- stage the next run of cells: thread <-> cell, elements compacted in (cell, frequency) order.  The run
         //      ends where the record buffer (NREC elements) or the table pool is full.
-        const int ncons = stage_pass<VARIANT>(a, cb, c_hi, f0, nf, s_rec, &s_w3[0][0], &s_w4[0][0], s_gcum, s_wsum, s_wlam, &s_tot,
-                                              &s_totlam);
+        const int ncons = stage_pass<VARIANT, THREADS>(a, cb, c_hi, f0, nf, s_rec, &s_w3[0][0], &s_w4[0][0], s_gcum, s_wsum, s_wlam, &s_tot,
+                                              &s_totlam
+#ifdef HOLO_PHASE_CLOCKS
+                                              , ph_last
+#endif
+                                              );
         const uint32_t pass_id = (uint32_t)cb;        // first cell of the run: names the pass in the Philox counter
         cb += ncons;
         __syncthreads();
+        HOLO_PHASE_MARK(0)   // staging
         const int nmain = (int)(s_tot & 2047u), ngrp = (int)((s_tot >> 11) & 2047u);
         const double glam_tot = s_totlam;
         // ---- per pass set-up shared by all realizations: CDF tables (one warp per table) and the PTRS list
@@ -494,6 +526,7 @@ realize_kernel(RealizeArgs a) {
             }
         }
         __syncthreads();
+        HOLO_PHASE_MARK(1)   // table builds
 
         // The RPT realization slots of a thread advance in lock-step through the records: they share the record
         // decode and the rung dispatch, and give the scheduler RPT independent dependency chains.
@@ -569,6 +602,7 @@ realize_kernel(RealizeArgs a) {
             }
         }
 
+        HOLO_PHASE_MARK(2)   // phase A (TABLE / NORMAL draws)
         // The two divergent stages take the slots one after the other in a run-time loop (one copy of the code);
         // their sums go through `tacc` and are merged into the slot's accumulators with static register indices.
         const int np = s_np;
@@ -596,7 +630,7 @@ realize_kernel(RealizeArgs a) {
                                key, [&](int member) {
                                    const int slot = NREC - 1 - member;
                                    const Rec rec = s_rec[slot];
-                                   if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, 1.0, &s_acc[0][0][SACC ? tid : 0] + u * RZ_THREADS, SACC_STRIDE);
+                                   if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, 1.0, &s_acc[0][0][SACC ? tid : 0] + u * THREADS, SACC_STRIDE);
                                    else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? slot : 0], s_w4[NACC > 4 ? slot : 0], f0, r, 1.0,
                                                           tacc, tvmax, timax);
                                });
@@ -614,7 +648,7 @@ realize_kernel(RealizeArgs a) {
                     double k;
                     const bool ok = ptrs_trial(pp, element_bits(key, idx, trial), &k);
                     if (ok) {
-                        if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, k, &s_acc[0][0][SACC ? tid : 0] + u * RZ_THREADS, SACC_STRIDE);
+                        if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, k, &s_acc[0][0][SACC ? tid : 0] + u * THREADS, SACC_STRIDE);
                         else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, k, tacc, tvmax, timax);
                         ++it;
                         trial = 0;
@@ -639,6 +673,7 @@ realize_kernel(RealizeArgs a) {
                 }
             }
         }
+        HOLO_PHASE_MARK(3)   // superposition group + PTRS
     }
 
 #pragma unroll
@@ -1027,7 +1062,7 @@ static Plan make_plan(int64_t ncell, int F, int R, int variant) {
     Plan p;
     const int rpt = rpt_for(variant, R);
     p.rpt = rpt;
-    p.threads = RZ_THREADS;   // always: the staging scan is one thread per cell of a 256-cell window (see stage_pass)
+    p.threads = threads_for(rpt, R);
     p.ntiles = (R + p.threads * rpt - 1) / (p.threads * rpt);
     p.nfg = (F + FGROUP - 1) / FGROUP;
     // The cell chunking must not depend on R (or on the realization tiling): per-chunk partial sums are
@@ -1094,34 +1129,46 @@ static Layout carve(void* ws, int variant, int64_t ncell, int F, int R, int cap,
     return l;
 }
 
-template <int VARIANT, int RPT>
+template <int VARIANT, int RPT, int THREADS>
 static int launch_realize_rpt(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
     dim3 grid(p.nfg, p.nchunk, p.ntiles);
     const bool sacc = nacc_of(VARIANT) == 1 && !has_max(VARIANT);
-    const size_t pool_bytes = sizeof(uint32_t) * POOL_ENTRIES + (sacc ? sizeof(double) * FGROUP * RPT * RZ_THREADS : 0) +
-                              sizeof(uint32_t) * 4 * RPT * RZ_THREADS;
+    const size_t pool_bytes = sizeof(uint32_t) * POOL_ENTRIES + (sacc ? sizeof(double) * FGROUP * RPT * THREADS : 0) +
+                              sizeof(uint32_t) * 4 * RPT * THREADS;
     static bool attr_set = false;   // static + dynamic shared memory may exceed the 48 KB default
     if (!attr_set) {
-        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
-        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
+        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
-    realize_kernel<VARIANT, RPT><<<grid, p.threads, pool_bytes, st>>>(ra); holo::count_launches(1);
+    realize_kernel<VARIANT, RPT, THREADS><<<grid, THREADS, pool_bytes, st>>>(ra); holo::count_launches(1);
     return holo_check_launch("realize_kernel");
 }
 
 template <int VARIANT>
 static int launch_realize(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
     if (flexible_rpt(VARIANT)) {
-        if (p.rpt == 4) return launch_realize_rpt<VARIANT, flexible_rpt(VARIANT) ? 4 : rpt_of(VARIANT)>(ra, p, st);
-        if (p.rpt == 2) return launch_realize_rpt<VARIANT, flexible_rpt(VARIANT) ? 2 : rpt_of(VARIANT)>(ra, p, st);
+        if (p.rpt == 4) return launch_realize_rpt<VARIANT, flexible_rpt(VARIANT) ? 4 : rpt_of(VARIANT), RZ_THREADS>(ra, p, st);
+        if (p.rpt == 2) return launch_realize_rpt<VARIANT, flexible_rpt(VARIANT) ? 2 : rpt_of(VARIANT), RZ_THREADS>(ra, p, st);
     }
-    return launch_realize_rpt<VARIANT, rpt_of(VARIANT)>(ra, p, st);
+    if (rpt_of(VARIANT) == 1 && p.threads == 128) return launch_realize_rpt<VARIANT, 1, 128>(ra, p, st);
+    return launch_realize_rpt<VARIANT, rpt_of(VARIANT), RZ_THREADS>(ra, p, st);
 }
 
 }  // namespace holo
 
 using namespace holo;
+
+#ifdef HOLO_PHASE_CLOCKS
+extern "C" int holo_debug_phase_clocks(unsigned long long* out8, int reset) {
+    if (out8) cudaMemcpyFromSymbol(out8, holo::g_phase_clk, sizeof(unsigned long long) * 8);
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyToSymbol(holo::g_phase_clk, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 extern "C" {
 
