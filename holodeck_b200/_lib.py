@@ -92,6 +92,10 @@ class LoudestArgs(C.Structure):
         ("workspace_bytes", C.c_int64),
         ("bucket_cap", C.c_int),
         ("head_margin", C.c_double),
+        ("gwb", C.c_void_p),
+        ("gwb_R", C.c_int),
+        ("gwb_r0", C.c_int64),
+        ("gwb_seed", C.c_uint64),
     ]
 
 
@@ -209,7 +213,7 @@ def load(path=None):
             raise HoloNativeError(f"{path} does not export `{name}`") from err
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.holo_abi_version() != 1:
+    if lib.holo_abi_version() != 2:
         raise HoloNativeError(f"ABI mismatch: library reports version {lib.holo_abi_version()}")
     _lib = lib
     return lib

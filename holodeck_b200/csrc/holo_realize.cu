@@ -108,6 +108,13 @@ struct RealizeArgs {
     // Philox counters use GLOBAL column indices so that a grid processed in column slabs (eccentric harmonics)
     // draws independently in every slab: frequency group fg + fg_key0, element index cell*F_key + f + f_key0
     int fg_key0, f_key0, F_key;
+    // Fused background slots (holo_loudest only): local realizations [R, R + Rg) draw an independent realised GWB
+    // (stream STREAM_GWB, seed k0g/k1g, global index r0g + (r - R)) from the same staged records and tables -- the
+    // work of a pass that does not depend on the realization is paid once for both products.
+    int Rg;
+    int64_t r0g;
+    uint32_t k0g, k1g;
+    double* partial_g;        // (nchunk, F, Rg)
 };
 
 // One staged ELEMENT (cell, frequency slot) with a non-zero expectation value.
@@ -176,7 +183,7 @@ static __device__ __noinline__ void push_event(const RealizeArgs& a, int f, int 
 template <int VARIANT, int FI>
 __device__ __forceinline__ void fold_static(const RealizeArgs& a, const Rec& rec, const double* w3, const double* w4,
                                             int f0, int r, double n, double (&acc)[FGROUP][nacc_of(VARIANT)],
-                                            double (&vmax)[FGROUP], int (&imax)[FGROUP]) {
+                                            double (&vmax)[FGROUP], int (&imax)[FGROUP], bool gslot) {
     constexpr int NACC = nacc_of(VARIANT);
     const double cur = rec.h;
     if (VARIANT == V_GWB) {
@@ -196,7 +203,7 @@ __device__ __forceinline__ void fold_static(const RealizeArgs& a, const Rec& rec
         }
     } else {
         // `if num < 1: continue` (pyx:1333, 1490, 1727): counts are integers (or > 1e10), so an empty draw adds zero
-        if (rec.meta & META_HEAD) {
+        if ((rec.meta & META_HEAD) && !gslot) {
             if (n >= 1.0) push_event(a, f0 + FI, r, rec.cell, n);
         } else {
             const double nc = n * cur;
@@ -216,12 +223,12 @@ __device__ __forceinline__ void fold_static(const RealizeArgs& a, const Rec& rec
 template <int VARIANT>
 __device__ __forceinline__ void fold_rec(const RealizeArgs& a, const Rec& rec, const double* w3, const double* w4,
                                          int f0, int r, double n, double (&acc)[FGROUP][nacc_of(VARIANT)],
-                                         double (&vmax)[FGROUP], int (&imax)[FGROUP]) {
+                                         double (&vmax)[FGROUP], int (&imax)[FGROUP], bool gslot = false) {
     switch (rec.meta & 3u) {
-        case 0: fold_static<VARIANT, 0>(a, rec, w3, w4, f0, r, n, acc, vmax, imax); break;
-        case 1: fold_static<VARIANT, 1>(a, rec, w3, w4, f0, r, n, acc, vmax, imax); break;
-        case 2: fold_static<VARIANT, 2>(a, rec, w3, w4, f0, r, n, acc, vmax, imax); break;
-        default: fold_static<VARIANT, 3>(a, rec, w3, w4, f0, r, n, acc, vmax, imax); break;
+        case 0: fold_static<VARIANT, 0>(a, rec, w3, w4, f0, r, n, acc, vmax, imax, gslot); break;
+        case 1: fold_static<VARIANT, 1>(a, rec, w3, w4, f0, r, n, acc, vmax, imax, gslot); break;
+        case 2: fold_static<VARIANT, 2>(a, rec, w3, w4, f0, r, n, acc, vmax, imax, gslot); break;
+        default: fold_static<VARIANT, 3>(a, rec, w3, w4, f0, r, n, acc, vmax, imax, gslot); break;
     }
 }
 
@@ -231,9 +238,9 @@ __device__ __forceinline__ void fold_rec(const RealizeArgs& a, const Rec& rec, c
 // SACC_STRIDE doubles apart.
 template <int VARIANT>
 __device__ __forceinline__ void fold_sacc(const RealizeArgs& a, const Rec& rec, int f0, int r, double n, double* col,
-                                          int stride) {
+                                          int stride, bool gslot = false) {
     const int fi = (int)(rec.meta & 3u);
-    if (has_events(VARIANT) && (rec.meta & META_HEAD)) {
+    if (has_events(VARIANT) && (rec.meta & META_HEAD) && !gslot) {
         if (n >= 1.0) push_event(a, f0 + fi, r, rec.cell, n);           // pyx:1333-1341
     } else {
         col[fi * stride] += n * rec.h;                                  // pyx:891-895, 1342
@@ -418,9 +425,10 @@ static __device__ __forceinline__ int stage_pass(const RealizeArgs& a, int64_t c
     return ncons;
 }
 
-template <int VARIANT, int RPT, int THREADS>
+template <int VARIANT, int RPT, int THREADS, bool FUSED>
 __global__ void __launch_bounds__(THREADS, min_ctas_of(VARIANT, RPT, THREADS))
 realize_kernel(RealizeArgs a) {
+    static_assert(!FUSED || has_events(VARIANT), "fused background slots exist in the loudest variants only");
     constexpr int NACC = nacc_of(VARIANT);
     constexpr int NREC = nrec_of(NACC);
     __shared__ __align__(16) Rec s_rec[NREC];           // main records grow from 0, group records from NREC-1 down
@@ -483,6 +491,21 @@ realize_kernel(RealizeArgs a) {
     key.real = 0;
     key.stream = has_events(VARIANT) ? STREAM_LOUD : (has_max(VARIANT) ? STREAM_SSBG : STREAM_GWB);
     const uint32_t real_first = (uint32_t)(a.r0 + r_first);
+    const int Rtot = a.R + (FUSED ? a.Rg : 0);       // live local realizations (incl. fused GWB slots)
+    // slot u of this thread: is it a fused background slot, and the Philox key of its realization
+    auto is_gslot = [&](int u) -> bool { return FUSED && (r_first + u * THREADS >= a.R); };
+    auto set_key = [&](int u) {
+        if (is_gslot(u)) {
+            key.k0 = a.k0g; key.k1 = a.k1g; key.stream = STREAM_GWB;
+            key.real = (uint32_t)(a.r0g + (r_first + u * THREADS - a.R));
+        } else {
+            if (FUSED) {
+                key.k0 = a.k0; key.k1 = a.k1;
+                key.stream = has_events(VARIANT) ? STREAM_LOUD : (has_max(VARIANT) ? STREAM_SSBG : STREAM_GWB);
+            }
+            key.real = real_first + (uint32_t)u * THREADS;
+        }
+    };
 
     int64_t cb = c_lo;
     HOLO_PHASE_DECL
@@ -546,7 +569,7 @@ realize_kernel(RealizeArgs a) {
             }
             continue;
         }
-        if (r_first >= a.R) continue;      // no live slot in this thread (the barriers are at the loop top)
+        if (r_first >= Rtot) continue;     // no live slot in this thread (the barriers are at the loop top)
 
         // ---- phase A, lock-step: every thread walks the main records; the (up to four) draws of a cell consume
         //      the words of one Philox block per slot, in record order
@@ -559,7 +582,7 @@ realize_kernel(RealizeArgs a) {
                 if (meta & META_FIRST) {
 #pragma unroll
                     for (int u = 0; u < RPT; ++u) {
-                        key.real = real_first + (uint32_t)u * blockDim.x;
+                        set_key(u);
                         const Philox4 hi = group_bits(key, (uint32_t)rec.cell, fgk, PURPOSE_GROUP_HI);
                         s_words[0][u][tid] = hi.v[0]; s_words[1][u][tid] = hi.v[1];     // (thread-private columns:
                         s_words[2][u][tid] = hi.v[2]; s_words[3][u][tid] = hi.v[3];     //  no synchronisation needed)
@@ -578,7 +601,7 @@ realize_kernel(RealizeArgs a) {
                     for (int u = 0; u < RPT; ++u) {
                         n[u] = (double)(int)(rec.kmin + (q[u] - rec.toff));
                         if (table_ambiguous(s_pool, rec.toff, W, q[u], word[u])) {
-                            key.real = real_first + (uint32_t)u * blockDim.x;
+                            set_key(u);
                             n[u] = table_resolve_keyed(rec.lam, s_pool + rec.toff, (int)rec.kmin, W, (int)(q[u] - rec.toff),
                                                        word[u], key, (uint32_t)rec.cell, fgk, ord);
                         }
@@ -587,7 +610,7 @@ realize_kernel(RealizeArgs a) {
                 } else {
 #pragma unroll
                     for (int u = 0; u < RPT; ++u) {
-                        key.real = real_first + (uint32_t)u * blockDim.x;
+                        set_key(u);
                         n[u] = draw_normal_lam(rec.lam, key, (uint64_t)(uint32_t)rec.cell * (uint64_t)a.F_key +
                                                              (uint64_t)(a.f_key0 + f0 + (int)(meta & 3u)));
                     }
@@ -595,9 +618,9 @@ realize_kernel(RealizeArgs a) {
 #pragma unroll
                 for (int u = 0; u < RPT; ++u) {
                     const int r = r_first + u * (int)blockDim.x;
-                    if (r >= a.R) continue;
-                    if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, n[u], &s_acc[0][SACC ? u : 0][SACC ? tid : 0], SACC_STRIDE);
-                    else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, n[u], acc[u], vmax[u], imax[u]);
+                    if (r >= Rtot) continue;
+                    if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, n[u], &s_acc[0][SACC ? u : 0][SACC ? tid : 0], SACC_STRIDE, is_gslot(u));
+                    else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, n[u], acc[u], vmax[u], imax[u], is_gslot(u));
                 }
             }
         }
@@ -610,8 +633,9 @@ realize_kernel(RealizeArgs a) {
 #pragma unroll 1
             for (int u = 0; u < RPT; ++u) {
                 const int r = r_first + u * (int)blockDim.x;
-                if (r >= a.R) break;
-                key.real = real_first + (uint32_t)u * blockDim.x;
+                if (r >= Rtot) break;
+                set_key(u);
+                const bool gslot = is_gslot(u);
                 double tacc[FGROUP][NACC];
                 double tvmax[FGROUP];
                 int timax[FGROUP];
@@ -630,9 +654,9 @@ realize_kernel(RealizeArgs a) {
                                key, [&](int member) {
                                    const int slot = NREC - 1 - member;
                                    const Rec rec = s_rec[slot];
-                                   if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, 1.0, &s_acc[0][0][SACC ? tid : 0] + u * THREADS, SACC_STRIDE);
+                                   if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, 1.0, &s_acc[0][0][SACC ? tid : 0] + u * THREADS, SACC_STRIDE, gslot);
                                    else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? slot : 0], s_w4[NACC > 4 ? slot : 0], f0, r, 1.0,
-                                                          tacc, tvmax, timax);
+                                                          tacc, tvmax, timax, gslot);
                                });
                 }
                 // ---- phase B, lane-decoupled: each lane walks the PTRS list at its own pace (one rejection trial
@@ -648,8 +672,8 @@ realize_kernel(RealizeArgs a) {
                     double k;
                     const bool ok = ptrs_trial(pp, element_bits(key, idx, trial), &k);
                     if (ok) {
-                        if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, k, &s_acc[0][0][SACC ? tid : 0] + u * THREADS, SACC_STRIDE);
-                        else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, k, tacc, tvmax, timax);
+                        if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, k, &s_acc[0][0][SACC ? tid : 0] + u * THREADS, SACC_STRIDE, gslot);
+                        else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? i : 0], s_w4[NACC > 4 ? i : 0], f0, r, k, tacc, tvmax, timax, gslot);
                         ++it;
                         trial = 0;
                     } else {
@@ -679,7 +703,16 @@ realize_kernel(RealizeArgs a) {
 #pragma unroll
     for (int t = 0; t < RPT; ++t) {
         const int r = r_first + t * (int)blockDim.x;
-        if (r >= a.R) continue;
+        if (r >= Rtot) continue;
+        if (FUSED && r >= a.R) {      // fused background slot: one sum per frequency
+#pragma unroll
+            for (int fi = 0; fi < FGROUP; ++fi) {
+                if (fi >= nf) break;
+                a.partial_g[((int64_t)chunk_id * a.F + f0 + fi) * a.Rg + (r - a.R)] =
+                    SACC ? s_acc[SACC ? fi : 0][SACC ? t : 0][SACC ? tid : 0] : acc[t][fi][0];
+            }
+            continue;
+        }
 #pragma unroll
         for (int fi = 0; fi < FGROUP; ++fi) {
             if (fi >= nf) break;
@@ -1129,20 +1162,26 @@ static Layout carve(void* ws, int variant, int64_t ncell, int F, int R, int cap,
     return l;
 }
 
-template <int VARIANT, int RPT, int THREADS>
-static int launch_realize_rpt(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
+template <int VARIANT, int RPT, int THREADS, bool FUSED>
+static int launch_realize_fused(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
     dim3 grid(p.nfg, p.nchunk, p.ntiles);
     const bool sacc = nacc_of(VARIANT) == 1 && !has_max(VARIANT);
     const size_t pool_bytes = sizeof(uint32_t) * POOL_ENTRIES + (sacc ? sizeof(double) * FGROUP * RPT * THREADS : 0) +
                               sizeof(uint32_t) * 4 * RPT * THREADS;
     static bool attr_set = false;   // static + dynamic shared memory may exceed the 48 KB default
     if (!attr_set) {
-        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
-        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT, THREADS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
+        HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT, THREADS, FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
-    realize_kernel<VARIANT, RPT, THREADS><<<grid, THREADS, pool_bytes, st>>>(ra); holo::count_launches(1);
+    realize_kernel<VARIANT, RPT, THREADS, FUSED><<<grid, THREADS, pool_bytes, st>>>(ra); holo::count_launches(1);
     return holo_check_launch("realize_kernel");
+}
+
+template <int VARIANT, int RPT, int THREADS>
+static int launch_realize_rpt(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
+    if (has_events(VARIANT) && ra.Rg > 0) return launch_realize_fused<VARIANT, RPT, THREADS, has_events(VARIANT)>(ra, p, st);
+    return launch_realize_fused<VARIANT, RPT, THREADS, false>(ra, p, st);
 }
 
 template <int VARIANT>
@@ -1250,11 +1289,20 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     const int64_t ncell = (int64_t)g->Mb * g->Qb * g->Zb;
     HOLO_REQUIRE(ncell < 2147483647LL, "holo_loudest: too many cells");
     const int F = g->F, R = g->R, L = g->L;
-    Plan p = make_plan(ncell, F, R, v);
+    // fused realised GWB: Rg extra background-only realization slots share the staged records and tables
+    const int Rg = g->gwb ? g->gwb_R : 0;
+    HOLO_REQUIRE(Rg >= 0 && (Rg == 0 || !g->counts), "holo_loudest: fused gwb needs gwb_R > 0 and no supplied counts");
+    Plan p = make_plan(ncell, F, R + Rg, v);            // slots per CTA / tiles from the total slot count
     double margin = g->head_margin > 0 ? g->head_margin : auto_margin(L);
     int cap = g->bucket_cap > 0 ? g->bucket_cap : auto_cap(L, margin);
     Layout l = carve(g->workspace, v, ncell, F, R, cap, p);
-    HOLO_REQUIRE(l.total <= g->workspace_bytes, "holo_loudest: workspace too small");
+    double* partial_g = nullptr;
+    int64_t ws_need = l.total;
+    if (Rg > 0) {       // tail of the workspace: holo_loudest_workspace_bytes(..) + holo_realize_workspace_bytes(GWB, .., Rg)
+        partial_g = reinterpret_cast<double*>(static_cast<unsigned char*>(g->workspace) + l.total);
+        ws_need += align256((int64_t)sizeof(double) * p.nchunk * F * Rg);
+    }
+    HOLO_REQUIRE(ws_need <= g->workspace_bytes, "holo_loudest: workspace too small");
     size_t res_smem = (size_t)RES_WARPS * 2 * cap * sizeof(Event);
     HOLO_REQUIRE(res_smem <= 200 * 1024, "holo_loudest: bucket_cap too large");
 
@@ -1290,6 +1338,8 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     ra.r0 = g->r0; ra.k0 = (uint32_t)g->seed; ra.k1 = (uint32_t)(g->seed >> 32);
     ra.thresh = (double)(int64_t)g->normal_threshold;
     ra.fg_key0 = 0; ra.f_key0 = 0; ra.F_key = F;
+    ra.Rg = Rg; ra.r0g = g->gwb_r0; ra.k0g = (uint32_t)g->gwb_seed; ra.k1g = (uint32_t)(g->gwb_seed >> 32);
+    ra.partial_g = partial_g;
     if (v == V_LOUD_PLAIN) rc = launch_realize<V_LOUD_PLAIN>(ra, p, st);
     else if (v == V_LOUD_PAR) rc = launch_realize<V_LOUD_PAR>(ra, p, st);
     else rc = launch_realize<V_LOUD_PAR_REDZ>(ra, p, st);
@@ -1327,6 +1377,12 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     else if (v == V_LOUD_PAR) final_kernel<V_LOUD_PAR><<<fblocks, FIN_R * FIN_SEG, 0, st>>>(fa);
     else final_kernel<V_LOUD_PAR_REDZ><<<fblocks, FIN_R * FIN_SEG, 0, st>>>(fa);
     holo::count_launches(1);
+    if (Rg > 0) {       // the fused background slots: same fixed-order chunk reduction as holo_sam_poisson_gwb
+        FinalArgs fg{};
+        fg.partial = partial_g; fg.out0 = g->gwb; fg.nchunk = p.nchunk; fg.Qb = 1; fg.Zb = 1; fg.F = F; fg.R = Rg;
+        const dim3 gblocks((Rg + FIN_R - 1) / FIN_R, F);
+        final_kernel<V_GWB><<<gblocks, FIN_R * FIN_SEG, 0, st>>>(fg); holo::count_launches(1);
+    }
     rc = holo_check_launch("holo_loudest: final");
     if (rc) return rc;
     timer.mark();

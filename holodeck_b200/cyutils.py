@@ -100,7 +100,7 @@ def sam_poisson_gwb(dist, hc2, nreals, normal_threshold=1e10, *, seed=None, coun
 
 def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold,
              mt=None, mr=None, rz=None, redz_final=None, dcom_final=None, sepa=None, angs=None,
-             seed=None, counts=None, r0=0):
+             seed=None, counts=None, r0=0, gwb_nreals=None, gwb_seed=None, gwb_r0=0):
     import torch
     lib = _lib.require_gpu()
     number = _lib.to_dev(number)
@@ -150,11 +150,22 @@ def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, norm
         out["bgpar"] = _lib.empty((7, F, R))
         args.sspar, args.bgpar = out["sspar"].data_ptr(), out["bgpar"].data_ptr()
 
+    # fused product: an independently drawn realised GWB of the same grid from the same pass (lib_tools.run_model)
+    Rg = 0 if gwb_nreals is None else int(gwb_nreals)
+    if Rg > 0:
+        assert cnt is None, "the fused GWB is not available in supplied-count mode"
+        out["gwb"] = _lib.empty((F, Rg))
+        args.gwb = out["gwb"].data_ptr()
+        args.gwb_R, args.gwb_r0, args.gwb_seed = Rg, int(gwb_r0), _seed(gwb_seed)
+
     cap, margin = 0, 0.0
     for attempt in range(_MAX_RETRY):
         args.bucket_cap = cap
         args.head_margin = margin
-        ws = _workspace(lib.holo_loudest_workspace_bytes(variant, ncell, F, R, L, cap))
+        nbytes = lib.holo_loudest_workspace_bytes(variant, ncell, F, R, L, cap)
+        if Rg > 0:
+            nbytes += lib.holo_realize_workspace_bytes(0, ncell, F, Rg)
+        ws = _workspace(nbytes)
         args.workspace = ws.data_ptr()
         args.workspace_bytes = ws.numel()
         rc = lib.holo_loudest(C.byref(args), _lib.stream())
@@ -171,7 +182,7 @@ def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, norm
 
 
 def loudest_hc_from_sorted(number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold=1e10, *,
-                           seed=None, counts=None, r0=0, device=False):
+                           seed=None, counts=None, r0=0, device=False, gwb_nreals=None, gwb_seed=None, gwb_r0=0):
     """Characteristic strain of the `nloudest` loudest single sources and of the background of all
     other sources (cyutils.pyx:1220-1344).
 
@@ -179,11 +190,14 @@ def loudest_hc_from_sorted(number, h2fdf, nreals, nloudest, msort, qsort, zsort,
     frequency (single_sources.py:89) -- and the first L binaries found take the L slots (a bin
     holding n binaries takes up to n slots); bins whose draw is < 1 are skipped entirely.
 
-    Returns ``hc2ss`` (F, R, L), ``hc2bg`` (F, R).
+    Returns ``hc2ss`` (F, R, L), ``hc2bg`` (F, R).  Keyword-only addition ``gwb_nreals``: the same pass over the
+    grid also draws that many independent realizations of the total GWB (what ``sam_poisson_gwb`` computes, own
+    ``gwb_seed``), appended to the result as ``gwb`` (F, gwb_nreals).
     """
     out = _loudest(1, number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold,
-                   seed=seed, counts=counts, r0=r0)
-    return _out(out["hc2ss"], device), _out(out["hc2bg"], device)
+                   seed=seed, counts=counts, r0=r0, gwb_nreals=gwb_nreals, gwb_seed=gwb_seed, gwb_r0=gwb_r0)
+    res = (_out(out["hc2ss"], device), _out(out["hc2bg"], device))
+    return res + ((_out(out["gwb"], device),) if "gwb" in out else ())
 
 
 def loudest_hc_and_par_from_sorted(number, h2fdf, nreals, nloudest, mt, mr, rz, msort, qsort, zsort,
@@ -201,18 +215,20 @@ def loudest_hc_and_par_from_sorted(number, h2fdf, nreals, nloudest, mt, mr, rz, 
 
 def loudest_hc_and_par_from_sorted_redz(number, h2fdf, nreals, nloudest, mt, mr, rz, redz_final, dcom_final,
                                         sepa, angs, msort, qsort, zsort, normal_threshold=1e10, *,
-                                        seed=None, counts=None, r0=0, device=False):
+                                        seed=None, counts=None, r0=0, device=False, gwb_nreals=None, gwb_seed=None,
+                                        gwb_r0=0):
     """As :func:`loudest_hc_from_sorted` for self-consistent hardening: per-source parameters
     ``sspar`` = (M, q, z_initial, z_final) and hc^2-weighted background means ``bgpar`` =
     (M, q, z_initial, z_final, d_c, a, theta) (cyutils.pyx:1541-1767).  Bins with ``h2fdf == 0`` are
     skipped (cyutils.pyx:1727).
 
-    Returns ``hc2ss`` (F,R,L), ``hc2bg`` (F,R), ``sspar`` (4,F,R,L), ``bgpar`` (7,F,R).
+    Returns ``hc2ss`` (F,R,L), ``hc2bg`` (F,R), ``sspar`` (4,F,R,L), ``bgpar`` (7,F,R) (and ``gwb`` (F, gwb_nreals)
+    with the keyword-only addition ``gwb_nreals``, see :func:`loudest_hc_from_sorted`).
     """
     out = _loudest(3, number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold,
                    mt=mt, mr=mr, rz=rz, redz_final=redz_final, dcom_final=dcom_final, sepa=sepa, angs=angs,
-                   seed=seed, counts=counts, r0=r0)
-    return tuple(_out(out[kk], device) for kk in ("hc2ss", "hc2bg", "sspar", "bgpar"))
+                   seed=seed, counts=counts, r0=r0, gwb_nreals=gwb_nreals, gwb_seed=gwb_seed, gwb_r0=gwb_r0)
+    return tuple(_out(out[kk], device) for kk in ("hc2ss", "hc2bg", "sspar", "bgpar") + (("gwb",) if "gwb" in out else ()))
 
 
 def _ss_bg(number, h2fdf, nreals, normal_threshold, mt=None, mr=None, rz=None, seed=None, counts=None, r0=0):

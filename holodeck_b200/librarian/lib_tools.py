@@ -348,12 +348,18 @@ def run_model(
         data['num_mtot_redz_final'] = num_mtot_redz_final
 
     # calculate single sources and/or binary parameters
+    fused_gwb = None
     if singles_flag or params_flag:
         nloudest = nloudest if singles_flag else 1
+        # the reference draws the GWB below independently of the loudest split (lib_tools.py:801-832); here the
+        # same pass of the realization kernel produces both, with independent Philox streams and seeds
         vals = single_sources.ss_gws_redz(
             edges, use_redz, number, realize=nreals, loudest=nloudest, params=params_flag,
             seed=None if sub is None else int(sub[0]), _precomputed=strain,
+            _gwb=(nreals, None if sub is None else int(sub[1])) if gwb_flag else None,
         )
+        if gwb_flag:
+            vals, fused_gwb = vals[:-1], vals[-1]
         if params_flag:
             hc_ss, hc_bg, sspar, bgpar = vals
             data['sspar'] = sspar
@@ -365,8 +371,11 @@ def run_model(
             data['hc_bg'] = hc_bg
 
     if gwb_flag:
-        gwb = gravwaves._gws_from_hc2(strain["h2fdf"], number, nreals, True,
-                                      None if sub is None else int(sub[1]), 0, False)
+        if fused_gwb is not None:
+            gwb = fused_gwb
+        else:
+            gwb = gravwaves._gws_from_hc2(strain["h2fdf"], number, nreals, True,
+                                          None if sub is None else int(sub[1]), 0, False)
         data['gwb'] = gwb
 
     return data

@@ -31,7 +31,7 @@ def _rank_order(h2fdf, shape):
 
 
 def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=None, r0=0, device=False,
-                _precomputed=None):
+                _precomputed=None, _gwb=None):
     """Strain of the `loudest` loudest single sources and of the background, per frequency and realization.
 
     Parameters mirror ``single_sources.ss_gws_redz`` (``single_sources.py:40-85``):
@@ -41,10 +41,13 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
 
     Returns ``hc_ss`` (F,R,L), ``hc_bg`` (F,R) and, if ``params``, ``sspar`` (4,F,R,L), ``bgpar`` (7,F,R)
     (numpy arrays; CUDA tensors with the keyword-only addition ``device=True``).
+    ``_gwb=(nreals, seed)`` (used by ``librarian.run_model``) appends ``gwb`` (F, nreals): the characteristic strain
+    of an independently drawn realised GWB of the same grid, produced by the same pass of the realization kernel.
     """
     import torch
     _lib.require_gpu()
     host = (lambda tt: tt) if device else _lib.to_host
+    gkw = {} if _gwb is None else dict(gwb_nreals=int(_gwb[0]), gwb_seed=_gwb[1])
     edges_np = [np.asarray(ee.cpu()) if _lib.is_device_array(ee) else np.asarray(ee, dtype=float) for ee in edges]
     # All other bin midpoints
     mt = utils.midpoints(edges_np[0])   #: total mass
@@ -74,10 +77,11 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
         raise Exception("`realize` ({}) must be an integer!")
 
     if params is True or params:
-        hc2ss, hc2bg, sspar, bgpar = cyutils.loudest_hc_and_par_from_sorted_redz(
+        hc2ss, hc2bg, sspar, bgpar, *extra = cyutils.loudest_hc_and_par_from_sorted_redz(
             number_d, h2fdf, realize, loudest,
             mt, mr, rz, strain["zmid"], strain["dcom"], strain["sepa"], strain["angs"],
-            msort, qsort, zsort, seed=seed, r0=r0, device=True)
+            msort, qsort, zsort, seed=seed, r0=r0, device=True, **gkw)
+        extra = tuple(host(torch.sqrt(ee)) for ee in extra)
         hc_ss = host(torch.sqrt(hc2ss))
         hc_bg = host(torch.sqrt(hc2bg))
         sspar = host(sspar)
@@ -88,13 +92,13 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
             err = int(bad.sum())
             err = f"check 1: {err} out of {sspar[3].size} sspar[3] are negative and not -1 in sings.ss_gws_redz()"
             raise ValueError(err)
-        return hc_ss, hc_bg, sspar, bgpar
+        return (hc_ss, hc_bg, sspar, bgpar) + extra
 
-    hc2ss, hc2bg = cyutils.loudest_hc_from_sorted(number_d, h2fdf, realize, loudest, msort, qsort, zsort,
-                                                  seed=seed, r0=r0, device=True)
+    hc2ss, hc2bg, *extra = cyutils.loudest_hc_from_sorted(number_d, h2fdf, realize, loudest, msort, qsort, zsort,
+                                                          seed=seed, r0=r0, device=True, **gkw)
     hc_ss = host(torch.sqrt(hc2ss))
     hc_bg = host(torch.sqrt(hc2bg))
-    return hc_ss, hc_bg
+    return (hc_ss, hc_bg) + tuple(host(torch.sqrt(ee)) for ee in extra)
 
 
 def ss_gws(edges, number, realize, loudest=1, params=False, *, seed=None, r0=0):

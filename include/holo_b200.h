@@ -34,7 +34,7 @@ extern "C" {
 #define HOLO_ERR_CUDA 2
 #define HOLO_ERR_OVERFLOW 3 /* loudest-source event buckets overflowed or head too short: retry bigger */
 
-#define HOLO_ABI_VERSION 1
+#define HOLO_ABI_VERSION 2
 
 int holo_abi_version(void);
 const char* holo_last_error(void);
@@ -248,6 +248,16 @@ typedef struct {
     int64_t workspace_bytes;
     int bucket_cap;         /* event-bucket capacity per (f,r); 0 = choose automatically */
     double head_margin;     /* expected occupied head cells beyond L; <=0 = automatic */
+    /* Optional fused product (ABI version 2).  lib_tools.run_model (librarian/lib_tools.py:801-832) asks for the
+     * loudest split AND an independently drawn realised GWB of the same grid; when `gwb` is non-NULL the same
+     * pass over the grid also draws `gwb_R` background-only realizations (own seed / global offset, stream of
+     * holo_sam_poisson_gwb) and writes gwb (F, gwb_R).  The workspace then needs
+     * holo_loudest_workspace_bytes(..) + holo_realize_workspace_bytes(HOLO_REALIZE_GWB, ncell, F, gwb_R) bytes.
+     * Not available in supplied-count mode. */
+    double* gwb;
+    int gwb_R;
+    int64_t gwb_r0;
+    uint64_t gwb_seed;
 } holo_loudest_args;
 
 /* Bytes of scratch `holo_loudest` needs for these sizes (bucket_cap 0 = automatic). */
