@@ -160,9 +160,9 @@ SIGNATURES = {
     "holo_dbn_gw": [CyConsts, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P],
     "holo_integrate_differential_number_3dx1d": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "holo_char_strain_sq": [C.POINTER(CosmoParams), _D, _D, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I,
-                            _P, _P, _P, _P, _P, _P],
+                            _P, _P, _P, _P, _P, _P, _P],
     "holo_integrate_and_strain": [C.POINTER(CosmoParams), _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                                  _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+                                  _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "holo_gwb_expectation": [_P, _P, _L, _I, _P, _P],
     "holo_sam_poisson_gwb": [_P, _P, _L, _I, _I, _L, _U, _D, _P, _P, _P, _L, _P],
     "holo_loudest_workspace_bytes": [_I, _L, _I, _I, _I, _I],

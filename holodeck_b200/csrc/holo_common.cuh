@@ -108,6 +108,39 @@ HOLO_HD double hard_func_2pwl(double norm, double xx, double gamma_inner, double
     return -norm * pow(1.0 + xx, -gamma_outer + gamma_inner) / pow(xx, gamma_inner - 1.0);
 }
 
+// x^e for the per-(z,f) evaluation of K1b: when 2e is a small integer (the library's gamma_inner = -1,
+// gamma_outer = +2.5 give e = -3.5 and e = -2) the power is a square root and a few multiplications (<= 3 ulp
+// from libm's pow, far inside the 1e-10 parity tolerance) instead of a ~150-instruction generic pow.
+struct HalfPow {
+    double e;
+    int n2;      // 2e when that is an integer with |2e| <= 32, else HALF_POW_GENERIC
+};
+constexpr int HALF_POW_GENERIC = 1 << 20;
+
+HOLO_HD HalfPow half_pow_spec(double e) {
+    HalfPow s;
+    s.e = e;
+    const double t = 2.0 * e;
+    s.n2 = (t == floor(t) && fabs(t) <= 32.0) ? (int)t : HALF_POW_GENERIC;
+    return s;
+}
+
+HOLO_HD double half_pow(double x, const HalfPow& s) {
+    if (s.n2 == HALF_POW_GENERIC) return pow(x, s.e);
+    const int n = s.n2 < 0 ? -s.n2 : s.n2;
+    double r = (n & 1) ? sqrt(x) : 1.0;
+    double b = x;
+    for (int m = n >> 1; m; m >>= 1) {
+        if (m & 1) r *= b;
+        b *= b;
+    }
+    return s.n2 < 0 ? 1.0 / r : r;
+}
+
+HOLO_HD double hard_func_2pwl_spec(double norm, double xx, const HalfPow& p_outer, const HalfPow& p_inner) {
+    return -norm * half_pow(1.0 + xx, p_outer) / half_pow(xx, p_inner);   // sam_cyutils.pyx:240-253
+}
+
 HOLO_HD double hard_func_2pwl_gw(const CyConsts& cc, double mtot, double mrat, double sepa, double norm,
                                  double rchar, double gamma_inner, double gamma_outer) {
     double dadt = hard_func_2pwl(norm, sepa / rchar, gamma_inner, gamma_outer);

@@ -261,6 +261,7 @@ HOLO_HD bool dbn_2pwl_cell_from(const CyConsts& cc, const MqConsts& mq, const Tr
                                 double gmt, double age_z, double ftarget, int lo, double* redz_out,
                                 double* dnum_out) {
     bool found = false;
+    const HalfPow p_outer = half_pow_spec(-gamma_outer + gamma_inner), p_inner = half_pow_spec(gamma_inner - 1.0);
     for (int s = lo; s < t.nsteps; ++s) {
         double time_right = t.tevo[s + 1] + gmt + age_z;               // pyx:659
         double time_left = time_right - t.dt[s];                       // pyx:661
@@ -282,7 +283,7 @@ HOLO_HD bool dbn_2pwl_cell_from(const CyConsts& cc, const MqConsts& mq, const Tr
         double dcom = interp_at_index(in, new_time, t.tage, t.gdc);
         double target_frst_orb = ftarget * (1.0 + new_redz);           // pyx:754
         double sepa = kepler_sepa_fast(mq, target_frst_orb);
-        double dadt = hard_func_2pwl(norm, sepa / rchar, gamma_inner, gamma_outer) + hard_gw_fast(mq, sepa);
+        double dadt = hard_func_2pwl_spec(norm, sepa / rchar, p_outer, p_inner) + hard_gw_fast(mq, sepa);
         double tres = -(2.0 / 3.0) * sepa / dadt;                      // pyx:764
         const double dmpc = dcom / CY_MPC;
         double cosmo_fact = cc.four_pi_c_over_mpc * (1.0 + new_redz) * (dmpc * dmpc);
@@ -353,12 +354,21 @@ HOLO_HD double integrate_bin(const double* dnum, int64_t sM, int64_t sQ, int64_t
 // =================================================================================================
 
 // three successive midpoint passes over axes 0,1,2 (gravwaves.py:705-708), -1 sentinels included
-HOLO_HD double corner_mean_redz(const double* rz, int64_t sM, int64_t sQ, int64_t sZ, int64_t base) {
+// `bad` (optional) reports a corner that is negative but not the -1 sentinel: the input check of
+// single_sources.py:95-99, done where the values are loaded anyway.
+HOLO_HD double corner_mean_redz(const double* rz, int64_t sM, int64_t sQ, int64_t sZ, int64_t base, bool* bad = nullptr) {
+    const double c000 = rz[base], c100 = rz[base + sM], c001 = rz[base + sZ], c101 = rz[base + sM + sZ];
+    const double c010 = rz[base + sQ], c110 = rz[base + sM + sQ], c011 = rz[base + sQ + sZ], c111 = rz[base + sM + sQ + sZ];
+    if (bad) {
+        *bad = (c000 < 0.0 && c000 != -1.0) || (c100 < 0.0 && c100 != -1.0) || (c001 < 0.0 && c001 != -1.0) ||
+               (c101 < 0.0 && c101 != -1.0) || (c010 < 0.0 && c010 != -1.0) || (c110 < 0.0 && c110 != -1.0) ||
+               (c011 < 0.0 && c011 != -1.0) || (c111 < 0.0 && c111 != -1.0);
+    }
     // axis 0
-    double a00 = 0.5 * (rz[base + sM] + rz[base]);
-    double a01 = 0.5 * (rz[base + sM + sZ] + rz[base + sZ]);
-    double a10 = 0.5 * (rz[base + sM + sQ] + rz[base + sQ]);
-    double a11 = 0.5 * (rz[base + sM + sQ + sZ] + rz[base + sQ + sZ]);
+    double a00 = 0.5 * (c100 + c000);
+    double a01 = 0.5 * (c101 + c001);
+    double a10 = 0.5 * (c110 + c010);
+    double a11 = 0.5 * (c111 + c011);
     // axis 1
     double b0 = 0.5 * (a10 + a00);
     double b1 = 0.5 * (a11 + a01);

@@ -100,7 +100,7 @@ def sam_poisson_gwb(dist, hc2, nreals, normal_threshold=1e10, *, seed=None, coun
 
 def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold,
              mt=None, mr=None, rz=None, redz_final=None, dcom_final=None, sepa=None, angs=None,
-             seed=None, counts=None, r0=0, gwb_nreals=None, gwb_seed=None, gwb_r0=0):
+             seed=None, counts=None, r0=0, gwb_nreals=None, gwb_seed=None, gwb_r0=0, order=None):
     import torch
     lib = _lib.require_gpu()
     number = _lib.to_dev(number)
@@ -109,7 +109,8 @@ def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, norm
     Mb, Qb, Zb, F = [int(ss) for ss in number.shape]
     ncell = Mb * Qb * Zb
     R, L = int(nreals), int(nloudest)
-    order = _order(msort, qsort, zsort, (Mb, Qb, Zb))
+    # `order` (keyword-only addition): the flat int32 rank order on the device, as `_order` would build it
+    order = _order(msort, qsort, zsort, (Mb, Qb, Zb)) if order is None else order
     assert order.numel() == ncell, "msort/qsort/zsort must list every (M,Q,Z) bin exactly once"
     cnt = _counts(counts, R, F, ncell)
 
@@ -182,7 +183,8 @@ def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, norm
 
 
 def loudest_hc_from_sorted(number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold=1e10, *,
-                           seed=None, counts=None, r0=0, device=False, gwb_nreals=None, gwb_seed=None, gwb_r0=0):
+                           seed=None, counts=None, r0=0, device=False, gwb_nreals=None, gwb_seed=None, gwb_r0=0,
+                           order=None):
     """Characteristic strain of the `nloudest` loudest single sources and of the background of all
     other sources (cyutils.pyx:1220-1344).
 
@@ -195,7 +197,7 @@ def loudest_hc_from_sorted(number, h2fdf, nreals, nloudest, msort, qsort, zsort,
     ``gwb_seed``), appended to the result as ``gwb`` (F, gwb_nreals).
     """
     out = _loudest(1, number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold,
-                   seed=seed, counts=counts, r0=r0, gwb_nreals=gwb_nreals, gwb_seed=gwb_seed, gwb_r0=gwb_r0)
+                   seed=seed, counts=counts, r0=r0, gwb_nreals=gwb_nreals, gwb_seed=gwb_seed, gwb_r0=gwb_r0, order=order)
     res = (_out(out["hc2ss"], device), _out(out["hc2bg"], device))
     return res + ((_out(out["gwb"], device),) if "gwb" in out else ())
 
@@ -216,7 +218,7 @@ def loudest_hc_and_par_from_sorted(number, h2fdf, nreals, nloudest, mt, mr, rz, 
 def loudest_hc_and_par_from_sorted_redz(number, h2fdf, nreals, nloudest, mt, mr, rz, redz_final, dcom_final,
                                         sepa, angs, msort, qsort, zsort, normal_threshold=1e10, *,
                                         seed=None, counts=None, r0=0, device=False, gwb_nreals=None, gwb_seed=None,
-                                        gwb_r0=0):
+                                        gwb_r0=0, order=None):
     """As :func:`loudest_hc_from_sorted` for self-consistent hardening: per-source parameters
     ``sspar`` = (M, q, z_initial, z_final) and hc^2-weighted background means ``bgpar`` =
     (M, q, z_initial, z_final, d_c, a, theta) (cyutils.pyx:1541-1767).  Bins with ``h2fdf == 0`` are
@@ -227,7 +229,7 @@ def loudest_hc_and_par_from_sorted_redz(number, h2fdf, nreals, nloudest, mt, mr,
     """
     out = _loudest(3, number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold,
                    mt=mt, mr=mr, rz=rz, redz_final=redz_final, dcom_final=dcom_final, sepa=sepa, angs=angs,
-                   seed=seed, counts=counts, r0=r0, gwb_nreals=gwb_nreals, gwb_seed=gwb_seed, gwb_r0=gwb_r0)
+                   seed=seed, counts=counts, r0=r0, gwb_nreals=gwb_nreals, gwb_seed=gwb_seed, gwb_r0=gwb_r0, order=order)
     return tuple(_out(out[kk], device) for kk in ("hc2ss", "hc2bg", "sspar", "bgpar") + (("gwb",) if "gwb" in out else ()))
 
 

@@ -22,12 +22,19 @@ def _rank_order(h2fdf, shape):
     Returns (msort, qsort, zsort) as CUDA int64 tensors.
     """
     import torch
+    indices = _rank_order_flat(h2fdf).to(dtype=torch.int64)
     _, Qb, Zb = shape
-    key = -h2fdf[..., 0].reshape(-1)
-    indices = torch.sort(key, stable=True).indices
     zsort = indices % Zb
     mq = indices // Zb
     return mq // Qb, mq % Qb, zsort
+
+
+def _rank_order_flat(h2fdf):
+    """The same order as :func:`_rank_order` as flat int32 bin indices ``(m*Q + q)*Z + z`` on the device -- what the
+    loudest kernels consume (the index triple of the reference's signature is only built when a caller asks)."""
+    import torch
+    key = -h2fdf[..., 0].reshape(-1)
+    return torch.sort(key, stable=True).indices.to(torch.int32)
 
 
 def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=None, r0=0, device=False,
@@ -66,12 +73,18 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
     h2fdf = strain["h2fdf"]
 
     # indices of bins sorted by h2fdf, just for the first frequency
-    msort, qsort, zsort = _rank_order(h2fdf, shape)
+    order = _rank_order_flat(h2fdf)
 
-    if bool(torch.any(torch.logical_and(redz_d < 0, redz_d != -1))):
-        err = int(torch.sum(torch.logical_and(redz_d < 0, redz_d != -1)))
-        err = f"{err} redz < 0 and !=-1 found in redz, in ss_gws_redz()"
-        raise ValueError(err)
+    # `redz` must be non-negative or the -1 sentinel (single_sources.py:95-99).  The strain kernel raises a flag
+    # while it reads the values (strains computed elsewhere are checked in separate passes); the flag is read after
+    # the draws, whose call synchronises anyway, so the check costs no extra pass and no extra stall.
+    def check_redz():
+        flag = strain.get("bad_redz")
+        if (flag is not None and int(flag.item()) != 0) or \
+                (flag is None and bool(torch.any(torch.logical_and(redz_d < 0, redz_d != -1)))):
+            err = int(torch.sum(torch.logical_and(redz_d < 0, redz_d != -1)))
+            err = f"{err} redz < 0 and !=-1 found in redz, in ss_gws_redz()"
+            raise ValueError(err)
 
     if not utils.isinteger(realize):
         raise Exception("`realize` ({}) must be an integer!")
@@ -80,7 +93,8 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
         hc2ss, hc2bg, sspar, bgpar, *extra = cyutils.loudest_hc_and_par_from_sorted_redz(
             number_d, h2fdf, realize, loudest,
             mt, mr, rz, strain["zmid"], strain["dcom"], strain["sepa"], strain["angs"],
-            msort, qsort, zsort, seed=seed, r0=r0, device=True, **gkw)
+            None, None, None, seed=seed, r0=r0, device=True, order=order, **gkw)
+        check_redz()
         extra = tuple(host(torch.sqrt(ee)) for ee in extra)
         hc_ss = host(torch.sqrt(hc2ss))
         hc_bg = host(torch.sqrt(hc2bg))
@@ -94,8 +108,9 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
             raise ValueError(err)
         return (hc_ss, hc_bg, sspar, bgpar) + extra
 
-    hc2ss, hc2bg, *extra = cyutils.loudest_hc_from_sorted(number_d, h2fdf, realize, loudest, msort, qsort, zsort,
-                                                          seed=seed, r0=r0, device=True, **gkw)
+    hc2ss, hc2bg, *extra = cyutils.loudest_hc_from_sorted(number_d, h2fdf, realize, loudest, None, None, None,
+                                                          seed=seed, r0=r0, device=True, order=order, **gkw)
+    check_redz()
     hc_ss = host(torch.sqrt(hc2ss))
     hc_bg = host(torch.sqrt(hc2bg))
     return (hc_ss, hc_bg) + tuple(host(torch.sqrt(ee)) for ee in extra)

@@ -265,3 +265,22 @@ def test_full_size_named_config_properties(holo):
     hi = sam.gwb(fobs_edges, hard, realize=R // 2, loudest=L, seed=77, r0=R // 2)
     assert np.array_equal(np.concatenate([lo[0], hi[0]], axis=1), hc_ss)
     assert np.array_equal(np.concatenate([lo[1], hi[1]], axis=1), hc_bg)
+
+
+def test_ss_gws_redz_rejects_bad_final_redshifts():
+    """`redz` values that are negative but not the -1 sentinel raise (single_sources.py:95-99); the check is a
+    flag raised by the strain kernel."""
+    import holodeck_b200 as holo
+    from holodeck_b200 import single_sources, utils
+    from holodeck_b200.constants import YR
+    rng = np.random.default_rng(5)
+    edges = [np.logspace(40, 43, 6), np.linspace(0.1, 1.0, 5), np.logspace(-2, 0.5, 7), utils.pta_freqs(10 * YR, 4)[1] / 2.0]
+    redz = rng.uniform(0.01, 2.0, size=(6, 5, 7, 4))
+    redz[rng.uniform(size=redz.shape) < 0.3] = -1.0
+    number = rng.uniform(0.0, 3.0, size=(5, 4, 6, 4))
+    hc_ss, hc_bg = single_sources.ss_gws_redz(edges, redz, number, realize=6, loudest=2, seed=1)
+    assert hc_ss.shape == (4, 6, 2) and np.all(np.isfinite(hc_bg))
+    bad = redz.copy()
+    bad[5, 4, 6, 3] = -0.25          # the very last grid point: a corner of exactly one bin
+    with pytest.raises(ValueError, match="1 redz < 0 and !=-1"):
+        single_sources.ss_gws_redz(edges, bad, number, realize=6, loudest=2, seed=1)
