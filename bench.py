@@ -72,7 +72,32 @@ class ClockSampler:
         self.proc = None
         self.lines = []
 
+    # NVML polled every 10 ms from a CHILD process (a sampling thread in this process would fight the step loop for
+    # the GIL and slow the very thing being timed); prints "unix_time,sm,max_sm,reasons" lines
+    NVML_CHILD = (
+        "import sys,time,pynvml as nv\n"
+        "nv.nvmlInit(); hh=nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))\n"
+        "bits={'hw_slowdown':nv.nvmlClocksThrottleReasonHwSlowdown,'hw_thermal_slowdown':nv.nvmlClocksThrottleReasonHwThermalSlowdown,"
+        "'sw_thermal_slowdown':nv.nvmlClocksThrottleReasonSwThermalSlowdown,'sw_power_cap':nv.nvmlClocksThrottleReasonSwPowerCap}\n"
+        "cmax=nv.nvmlDeviceGetMaxClockInfo(hh,nv.NVML_CLOCK_SM)\n"
+        "print('ready',flush=True)\n"
+        "while True:\n"
+        "    rr=int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(hh))\n"
+        "    print(time.time(),nv.nvmlDeviceGetClockInfo(hh,nv.NVML_CLOCK_SM),cmax,'|'.join(k for k,b in bits.items() if rr&b),sep=',',flush=True)\n"
+        "    time.sleep(0.01)\n")
+
     def start(self):
+        self.samples, self.nvml = [], False
+        try:
+            import pynvml  # noqa: F401
+            self.proc = subprocess.Popen([sys.executable, "-c", self.NVML_CHILD, str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            if self.proc.stdout.readline().strip() == "ready":
+                self.nvml = True      # its output waits in the pipe (a few KB) until stop(): no reader thread either
+                return
+            self.proc.kill()
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
@@ -87,6 +112,20 @@ class ClockSampler:
             self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self, t0, t1):
+        if getattr(self, "nvml", False):
+            time.sleep(0.03)
+            self.proc.terminate()
+            for line in self.proc.stdout.read().splitlines():
+                parts = line.strip().split(",")
+                if len(parts) == 4:
+                    self.samples.append((float(parts[0]), float(parts[1]), float(parts[2]), [rr for rr in parts[3].split("|") if rr]))
+            # t0, t1 are perf_counter values: map the child's unix times onto them
+            off = time.time() - time.perf_counter()
+            inside = [ss for ss in self.samples if t0 <= ss[0] - off <= t1] or self.samples
+            reasons = sorted({nn for ss in inside for nn in ss[3]})
+            return {"sm_mhz": float(np.median([ss[1] for ss in inside])) if inside else None,
+                    "sm_max_mhz": inside[0][2] if inside else None, "reasons": reasons, "samples": len(inside),
+                    "source": "nvml polled every 10 ms by a child process; samples inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

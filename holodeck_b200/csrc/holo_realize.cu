@@ -63,16 +63,46 @@ static_assert(FGROUP * (TABLE_WMAX + 2) + GROUP_RESERVE <= POOL_ENTRIES, "one ce
 // clock64 cycles it spends in each phase of a pass to g_phase_clk (read with holo_debug_phase_clocks).
 #ifdef HOLO_PHASE_CLOCKS
 __device__ unsigned long long g_phase_clk[8];
+__device__ unsigned long long g_item_phase[16384][8];   // the same per (chunk, frequency group) item
+__device__ unsigned long long g_cta_span[4][16384];   // globaltimer at start / end, SM id and work item of each CTA
+__device__ __forceinline__ unsigned long long holo_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned holo_smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+#define HOLO_CTA_ITEM(item)                                                                          \
+    if (threadIdx.x == 0) {                                                                          \
+        const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);         \
+        if (lin < 16384u) g_cta_span[3][lin] = (unsigned long long)(item);                           \
+    }
+#define HOLO_CTA_SPAN(which)                                                                         \
+    if (threadIdx.x == 0) {                                                                          \
+        const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);         \
+        if (lin < 16384u) {                                                                          \
+            g_cta_span[which][lin] = holo_globaltimer();                                             \
+            g_cta_span[2][lin] = holo_smid();                                                        \
+        }                                                                                            \
+    }
 #define HOLO_PHASE_DECL long long ph_last = clock64();
 #define HOLO_PHASE_MARK(i)                                                          \
     if (threadIdx.x == 0) {                                                         \
         const long long ph_now = clock64();                                         \
         atomicAdd(&g_phase_clk[i], (unsigned long long)(ph_now - ph_last));         \
+        const unsigned ph_lin = blockIdx.x + gridDim.x * blockIdx.y;                \
+        const unsigned ph_item = a.order ? (unsigned)a.order[ph_lin] : ph_lin;      \
+        if (ph_item < 16384u) atomicAdd(&g_item_phase[ph_item][i], (unsigned long long)(ph_now - ph_last)); \
         ph_last = ph_now;                                                           \
     }
 #else
 #define HOLO_PHASE_DECL
 #define HOLO_PHASE_MARK(i)
+#define HOLO_CTA_SPAN(which)
+#define HOLO_CTA_ITEM(item)
 #endif
 
 struct Event {
@@ -111,6 +141,7 @@ struct RealizeArgs {
     // Fused background slots (holo_loudest only): local realizations [R, R + Rg) draw an independent realised GWB
     // (stream STREAM_GWB, seed k0g/k1g, global index r0g + (r - R)) from the same staged records and tables -- the
     // work of a pass that does not depend on the realization is paid once for both products.
+    const int32_t* order;     // (nchunk * nfg,) launch order of the (chunk, frequency group) items, heaviest first; or NULL
     int Rg;
     int64_t r0g;
     uint32_t k0g, k1g;
@@ -168,6 +199,9 @@ __device__ __forceinline__ void load_group(const double* __restrict__ base, int 
 // An occupied head cell of the loudest variants: append (rank, cell, n) to the (f, r) event bucket.  Out of
 // line: rare (a few dozen per (f, r)) and it keeps the hot loops small.
 static __device__ __noinline__ void push_event(const RealizeArgs& a, int f, int r, int cell, double n) {
+#ifdef HOLO_NO_PUSH
+    return;      // (profiling experiment only: results are wrong)
+#endif
     const int slot = atomicAdd(&a.evcount[(int64_t)f * a.R + r], 1);
     if (slot < a.cap) {
         Event ev;
@@ -247,28 +281,37 @@ __device__ __forceinline__ void fold_sacc(const RealizeArgs& a, const Rec& rec, 
     }
 }
 
-// One warp tabulates the CDF of Poisson(lam) over its window as 32-bit thresholds (see holo_rng.cuh);
-// t[-1] = 0 and t[W] = 2^32-1 are sentinels for the ambiguity test of the draw.
-static __device__ __noinline__ void build_table_warp(double lam, uint32_t* t, int kmin, int W, int lane) {
-    const int seg = (W + 31) >> 5;
-    int j0 = lane * seg;
+// SW cooperating lanes tabulate the CDF of Poisson(lam) over its window as 32-bit thresholds (see holo_rng.cuh);
+// t[-1] = 0 and t[W] = 2^32-1 are sentinels for the ambiguity test of the draw.  The 32/SW sub-warps of a warp build
+// DIFFERENT tables at the same time (`sl` = lane within the sub-warp; every lane of the warp must call, inactive
+// sub-warps with active = false): most tables have fewer than 64 entries, so the cost of a table is the one pmf
+// evaluation per lane (log, exp, Stirling) and the scan, not the entries -- narrow sub-warps cut that latency 4x.
+template <int SW>
+static __device__ __noinline__ void build_table_sub(double lam, uint32_t* t, int kmin, int W, int sl, bool active) {
+    const int seg = (W + SW - 1) / SW;
+    int j0 = sl * seg;
     if (j0 > W) j0 = W;
     int j1 = j0 + seg;
     if (j1 > W) j1 = W;
+    if (!active) {
+        j0 = j1 = 0;
+        lam = 1.0;
+    }
     const double ln_lam = log(lam), inv_lam = 1.0 / lam;
     double ptop;
     double incl = table_segment_mass(lam, ln_lam, inv_lam, kmin, j0, j1, &ptop);
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const double v = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += v;
+    for (int off = 1; off < SW; off <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, incl, off, SW);
+        if (sl >= off) incl += v;
     }
     table_segment_write(t, incl, ptop, inv_lam, kmin, j0, j1);
-    if (lane == 0) {
+    if (active && sl == 0) {
         t[-1] = 0u;
         t[W] = 0xFFFFFFFFu;
     }
 }
+constexpr int BUILD_SW = 8;      // lanes per element table
 
 // Stage the next run of cells of a pass (see the kernel): thread <-> cell, elements compacted in (cell, frequency)
 // order into `s_rec` (main records from 0 up, group members from NREC-1 down).  Returns the number of cells
@@ -446,8 +489,16 @@ realize_kernel(RealizeArgs a) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarp = blockDim.x >> 5;
-    const int fg = blockIdx.x;          // fastest: the CTAs sharing a chunk's 320 B rows run together (L2 reuse)
-    const int chunk_id = blockIdx.y;
+    // CTAs start in launch-index order (x fastest).  The work of an item -- a (cell chunk, frequency group) pair --
+    // ranges over three orders of magnitude (low masses at the lowest frequencies hold nearly all the tables), so the
+    // items are handed out heaviest first (`order`, see cost_kernel): without it a handful of 9 ms CTAs that start
+    // late leave most SMs idle for the last quarter of the kernel.
+    int fg = blockIdx.x, chunk_id = blockIdx.y;
+    if (a.order != nullptr) {
+        const int item = a.order[blockIdx.y * gridDim.x + blockIdx.x];
+        fg = item % (int)gridDim.x;
+        chunk_id = item / (int)gridDim.x;
+    }
     const int f0 = fg * FGROUP;
     const uint32_t fgk = (uint32_t)(fg + a.fg_key0);   // global frequency-group index (Philox counter)
     const int r_first = blockIdx.z * (blockDim.x * RPT) + tid;      // local realization of slot t = 0
@@ -508,6 +559,8 @@ realize_kernel(RealizeArgs a) {
     };
 
     int64_t cb = c_lo;
+    HOLO_CTA_SPAN(0)
+    HOLO_CTA_ITEM(chunk_id * (int)gridDim.x + fg)
     HOLO_PHASE_DECL
     while (cb < c_hi) {
         // ---- stage the next run of cells: thread <-> cell, elements compacted in (cell, frequency) order.  The run
@@ -526,14 +579,17 @@ realize_kernel(RealizeArgs a) {
         const double glam_tot = s_totlam;
         // ---- per pass set-up shared by all realizations: CDF tables (one warp per table) and the PTRS list
         if (!supplied) {
-            for (int i = warp; i < nmain; i += nwarp) {
-                const Rec& rec = s_rec[i];
-                if (((rec.meta >> 2) & 7u) != CLS_TABLE) continue;
-                build_table_warp(rec.lam, s_pool + rec.toff, (int)rec.kmin, (int)((rec.meta >> 12) & 4095u), lane);
+            constexpr int NSUB = 32 / BUILD_SW;
+            const int sub = lane / BUILD_SW, sl = lane % BUILD_SW;
+            for (int base = warp * NSUB; base < nmain; base += nwarp * NSUB) {      // (warp-uniform trip count)
+                const int i = base + sub;
+                const bool act = (i < nmain) && (((s_rec[i < nmain ? i : 0].meta >> 2) & 7u) == CLS_TABLE);
+                const Rec& rec = s_rec[act ? i : 0];
+                build_table_sub<BUILD_SW>(rec.lam, s_pool + rec.toff, (int)rec.kmin, (int)((rec.meta >> 12) & 4095u), sl, act);
             }
             if (warp == nwarp - 1 && ngrp > 0) {
                 const TableSpec ts = table_spec(glam_tot);
-                build_table_warp(glam_tot, s_pool + 1, ts.kmin, ts.W, lane);
+                build_table_sub<32>(glam_tot, s_pool + 1, ts.kmin, ts.W, lane, true);
                 if (lane == 0) { s_gspec[0] = ts.kmin; s_gspec[1] = ts.W; s_gspec[2] = 31 - __clz(ts.W); }
             }
             if (warp == 0) {
@@ -650,14 +706,36 @@ realize_kernel(RealizeArgs a) {
                 //      process of rate Lambda = sum lam_k; each of its N events belongs to member k with
                 //      probability lam_k / Lambda (exact: superposition / thinning of Poisson processes)
                 if (ngrp > 0) {
+                    // Events of HEAD members are parked (six 10-bit record indices in one 64-bit word) and appended to
+                    // the buckets after the event loop.  Appending inside the loop makes every turn of the loop in which
+                    // ANY lane holds such an event wait for a global atomic's round trip: passes whose group is made of
+                    // head cells ran ten times longer (measured), and those ~100 CTAs were the tail of the kernel.
+                    unsigned long long pend = 0ull;
+                    int npend = 0;
+                    auto flush = [&]() {
+                        while (npend > 0) {
+                            const Rec rec = s_rec[(int)(pend & 1023ull)];
+                            push_event(a, f0 + (int)(rec.meta & 3u), r, rec.cell, 1.0);
+                            pend >>= 10;
+                            --npend;
+                        }
+                    };
                     draw_group(s_pool, 1u, s_gspec[0], s_gspec[1], s_gspec[2], glam_tot, s_gcum, ngrp, pass_id, fgk,
                                key, [&](int member) {
                                    const int slot = NREC - 1 - member;
                                    const Rec rec = s_rec[slot];
-                                   if (SACC) fold_sacc<VARIANT>(a, rec, f0, r, 1.0, &s_acc[0][0][SACC ? tid : 0] + u * THREADS, SACC_STRIDE, gslot);
-                                   else fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? slot : 0], s_w4[NACC > 4 ? slot : 0], f0, r, 1.0,
-                                                          tacc, tvmax, timax, gslot);
+                                   if (has_events(VARIANT) && (rec.meta & META_HEAD) && !gslot) {
+                                       if (npend == 6) flush();
+                                       pend = (pend << 10) | (unsigned long long)slot;
+                                       ++npend;
+                                   } else if (SACC) {
+                                       fold_sacc<VARIANT>(a, rec, f0, r, 1.0, &s_acc[0][0][SACC ? tid : 0] + u * THREADS, SACC_STRIDE, gslot);
+                                   } else {
+                                       fold_rec<VARIANT>(a, rec, s_w3[NACC > 1 ? slot : 0], s_w4[NACC > 4 ? slot : 0], f0, r, 1.0,
+                                                         tacc, tvmax, timax, gslot);
+                                   }
                                });
+                    if (has_events(VARIANT)) flush();
                 }
                 // ---- phase B, lane-decoupled: each lane walks the PTRS list at its own pace (one rejection trial
                 //      per loop turn), so a rejected proposal delays only its own lane
@@ -699,6 +777,7 @@ realize_kernel(RealizeArgs a) {
         }
         HOLO_PHASE_MARK(3)   // superposition group + PTRS
     }
+    HOLO_CTA_SPAN(1)
 
 #pragma unroll
     for (int t = 0; t < RPT; ++t) {
@@ -728,6 +807,72 @@ realize_kernel(RealizeArgs a) {
             }
         }
     }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Launch order of the realization kernel: longest-processing-time-first list scheduling.
+// cost_kernel estimates the work of every (chunk, frequency group) item from the sampler classes of its elements
+// (a table draw = 16 units, a PTRS draw = 64, a member of a superposition group = 1: measured CTA durations follow
+// this to R^2 = 0.998, and the makespan is insensitive to the weights) and histograms the items over COST_BINS
+// logarithmic cost classes; order_kernel scatters them heaviest class first.  The order within a class is left to
+// the atomics: it only decides WHEN an item runs, never what it computes.
+// -------------------------------------------------------------------------------------------------
+constexpr int COST_BINS = 256;     // 8 classes per octave
+
+__device__ __forceinline__ int cost_bin(uint32_t c) {     // c >= 1
+    const int lz = 31 - __clz(c);
+    const uint32_t sub = lz >= 3 ? ((c >> (lz - 3)) & 7u) : ((c << (3 - lz)) & 7u);
+    return lz * 8 + (int)sub;
+}
+
+__global__ void __launch_bounds__(256)
+cost_kernel(const double* __restrict__ number, int64_t ncell, int F, int64_t chunk, int nfg, double thresh,
+            const int32_t* __restrict__ rank, const int32_t* __restrict__ kf, double head_weight,
+            uint32_t* __restrict__ cost, uint32_t* __restrict__ hist) {
+    extern __shared__ uint32_t s_cost[];     // (nfg,)
+    for (int i = threadIdx.x; i < nfg; i += blockDim.x) s_cost[i] = 0u;
+    __syncthreads();
+    const int64_t c_lo = (int64_t)blockIdx.x * chunk;
+    int64_t c_hi = c_lo + chunk;
+    if (c_hi > ncell) c_hi = ncell;
+    const int64_t n = (c_hi - c_lo) * F;
+    const double* base = number + c_lo * F;
+    for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+        const double lam = base[e];
+        if (!(lam > 0.0)) continue;
+        uint32_t w = lam < GROUP_MAX_LAM ? 1u : ((lam <= TABLE_MAX_LAM || lam > thresh) ? 16u : 64u);
+        const int f = (int)(e % F);
+        // an occupied head cell of the loudest variants appends an event per realization (a global atomic and a
+        // dependent 16 B store, out of line).  Measured: the ~100 items that hold the occupied head cells run 2-3 ms
+        // longer than their tables predict (0.6 ms per expected event per realization at 1024 realizations per CTA);
+        // left unweighted they start late and ARE the tail of the kernel.  Overweighting only starts them earlier.
+        if (rank != nullptr && rank[c_lo + e / F] < kf[f]) w += 32u + (uint32_t)(head_weight * (lam >= 1.0 ? 1.0 : lam));
+        atomicAdd(&s_cost[f / FGROUP], w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nfg; i += blockDim.x) {
+        const uint32_t c = s_cost[i] + 1u;
+        cost[(int64_t)blockIdx.x * nfg + i] = c;
+        atomicAdd(&hist[cost_bin(c)], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+order_kernel(const uint32_t* __restrict__ cost, const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, int n,
+             int32_t* __restrict__ order) {
+    __shared__ uint32_t s_first[COST_BINS];     // first position of each class, heaviest class first
+    if (threadIdx.x == 0) {
+        uint32_t run = 0u;
+        for (int b = COST_BINS - 1; b >= 0; --b) {
+            s_first[b] = run;
+            run += hist[b];
+        }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = cost_bin(cost[i]);
+    order[s_first[b] + atomicAdd(&cursor[b], 1u)] = i;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1136,6 +1281,7 @@ struct Workspace {
 struct Layout {
     double* partial; double* pmax; int32_t* pidx; Event* events; int32_t* evcount; double* rem;
     int32_t* flags; int32_t* kf; int32_t* rank; double* bsum;
+    int32_t* order; uint32_t* cost; uint32_t* hist;   // launch order of the realization kernel (hist: 2 x COST_BINS)
     int64_t total;
 };
 
@@ -1158,8 +1304,25 @@ static Layout carve(void* ws, int variant, int64_t ncell, int F, int R, int cap,
         int nblk = (int)((ncell + HEAD_ROWS - 1) / HEAD_ROWS);
         l.bsum = (double*)w.take(sizeof(double) * (int64_t)nblk * F);
     }
+    const int64_t nitem = (int64_t)p.nchunk * p.nfg;
+    l.order = (int32_t*)w.take(sizeof(int32_t) * nitem);
+    l.cost = (uint32_t*)w.take(sizeof(uint32_t) * nitem);
+    l.hist = (uint32_t*)w.take(sizeof(uint32_t) * 2 * COST_BINS);
     l.total = w.used;
     return l;
+}
+
+// fills l.order (heaviest items first) on `st`
+static int plan_launch_order(const double* number, int64_t ncell, int F, double thresh, const int32_t* rank,
+                             const int32_t* kf, int R, const Plan& p, const Layout& l, cudaStream_t st) {
+    const int per_cta = R < p.threads * p.rpt ? R : p.threads * p.rpt;     // realizations one CTA carries
+    const double head_weight = 8.0 * per_cta;
+    const int n = p.nchunk * p.nfg;
+    HOLO_CUDA(cudaMemsetAsync(l.hist, 0, sizeof(uint32_t) * 2 * COST_BINS, st));
+    cost_kernel<<<p.nchunk, 256, sizeof(uint32_t) * p.nfg, st>>>(number, ncell, F, p.chunk, p.nfg, thresh, rank, kf, head_weight, l.cost, l.hist);
+    order_kernel<<<(n + 255) / 256, 256, 0, st>>>(l.cost, l.hist, l.hist + COST_BINS, n, l.order);
+    holo::count_launches(2);
+    return holo_check_launch("realization launch order");
 }
 
 template <int VARIANT, int RPT, int THREADS, bool FUSED>
@@ -1207,6 +1370,18 @@ extern "C" int holo_debug_phase_clocks(unsigned long long* out8, int reset) {
     }
     return 0;
 }
+extern "C" int holo_debug_item_phases(unsigned long long* out16384x8, int reset) {
+    int rc = (int)cudaMemcpyFromSymbol(out16384x8, holo::g_item_phase, sizeof(unsigned long long) * 16384 * 8);
+    if (reset) {
+        void* p = nullptr;
+        cudaGetSymbolAddress(&p, holo::g_item_phase);
+        cudaMemset(p, 0, sizeof(unsigned long long) * 16384 * 8);
+    }
+    return rc;
+}
+extern "C" int holo_debug_cta_spans(unsigned long long* out4x16384) {
+    return (int)cudaMemcpyFromSymbol(out4x16384, holo::g_cta_span, sizeof(unsigned long long) * 4 * 16384);
+}
 #endif
 
 extern "C" {
@@ -1250,7 +1425,10 @@ int realize_gwb_columns(const double* number, const double* h2fdf, int64_t ncell
     ra.fg_key0 = key_col0 / FGROUP; ra.f_key0 = key_col0; ra.F_key = key_cols > 0 ? key_cols : F;
     StageTimer timer(st);
     timer.mark();
-    int rc = launch_realize<V_GWB>(ra, p, st);
+    int rc = plan_launch_order(number, ncell, F, ra.thresh, nullptr, nullptr, R, p, l, st);
+    if (rc) return rc;
+    ra.order = l.order;
+    rc = launch_realize<V_GWB>(ra, p, st);
     if (rc) return rc;
     timer.mark();
     FinalArgs fa{};
@@ -1340,6 +1518,9 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     ra.fg_key0 = 0; ra.f_key0 = 0; ra.F_key = F;
     ra.Rg = Rg; ra.r0g = g->gwb_r0; ra.k0g = (uint32_t)g->gwb_seed; ra.k1g = (uint32_t)(g->gwb_seed >> 32);
     ra.partial_g = partial_g;
+    rc = plan_launch_order(g->number, ncell, F, ra.thresh, l.rank, l.kf, R, p, l, st);
+    if (rc) return rc;
+    ra.order = l.order;
     if (v == V_LOUD_PLAIN) rc = launch_realize<V_LOUD_PLAIN>(ra, p, st);
     else if (v == V_LOUD_PAR) rc = launch_realize<V_LOUD_PAR>(ra, p, st);
     else rc = launch_realize<V_LOUD_PAR_REDZ>(ra, p, st);
@@ -1423,7 +1604,10 @@ int holo_ss_bg_hc(const double* number, const double* h2fdf, int Mb, int Qb, int
     ra.r0 = r0; ra.k0 = (uint32_t)seed; ra.k1 = (uint32_t)(seed >> 32);
     ra.thresh = (double)(int64_t)normal_threshold;
     ra.fg_key0 = 0; ra.f_key0 = 0; ra.F_key = F;
-    int rc = par ? launch_realize<V_SSBG_PAR>(ra, p, st) : launch_realize<V_SSBG>(ra, p, st);
+    int rc = plan_launch_order(number, ncell, F, ra.thresh, nullptr, nullptr, R, p, l, st);
+    if (rc) return rc;
+    ra.order = l.order;
+    rc = par ? launch_realize<V_SSBG_PAR>(ra, p, st) : launch_realize<V_SSBG>(ra, p, st);
     if (rc) return rc;
     FinalArgs fa{};
     fa.partial = l.partial; fa.pmax = l.pmax; fa.pidx = l.pidx; fa.h2fdf = h2fdf;

@@ -235,23 +235,24 @@ void emu_draw_group(const double* lam4, int64_t n, uint64_t seed, double thresh,
     }
 }
 
-// 32-lane emulation of build_table_warp (holo_realize.cu): thresholds at t[0..W), sentinels at t[-1], t[W]
-static void emu_build_table(double lam, uint32_t* t, int kmin, int W) {
-    const int seg = (W + 31) >> 5;
+// lane-by-lane emulation of build_table_sub<SW> (holo_realize.cu; SW = 8 lanes per element table, 32 for the table of
+// a superposition group): thresholds at t[0..W), sentinels at t[-1], t[W]
+static void emu_build_table(double lam, uint32_t* t, int kmin, int W, int SW = 8) {
+    const int seg = (W + SW - 1) / SW;
     const double ln_lam = log(lam), inv_lam = 1.0 / lam;
     double incl[32], ptop[32];
     int j0[32], j1[32];
-    for (int l = 0; l < 32; ++l) {
+    for (int l = 0; l < SW; ++l) {
         j0[l] = l * seg > W ? W : l * seg;
         j1[l] = j0[l] + seg > W ? W : j0[l] + seg;
         incl[l] = table_segment_mass(lam, ln_lam, inv_lam, kmin, j0[l], j1[l], &ptop[l]);
     }
-    for (int off = 1; off < 32; off <<= 1) {
+    for (int off = 1; off < SW; off <<= 1) {
         double prev[32];
-        for (int l = 0; l < 32; ++l) prev[l] = incl[l];
-        for (int l = off; l < 32; ++l) incl[l] = prev[l] + prev[l - off];
+        for (int l = 0; l < SW; ++l) prev[l] = incl[l];
+        for (int l = off; l < SW; ++l) incl[l] = prev[l] + prev[l - off];
     }
-    for (int l = 0; l < 32; ++l) table_segment_write(t, incl[l], ptop[l], inv_lam, kmin, j0[l], j1[l]);
+    for (int l = 0; l < SW; ++l) table_segment_write(t, incl[l], ptop[l], inv_lam, kmin, j0[l], j1[l]);
     t[-1] = 0u;
     t[W] = 0xFFFFFFFFu;
 }
@@ -302,7 +303,7 @@ void emu_draw_group_members(const double* lam, int K, int64_t n, uint64_t seed, 
     for (int k = 0; k < K; ++k) { c += lam[k]; gcum[k] = c; }
     const TableSpec ts = table_spec(c);
     std::vector<uint32_t> tab(ts.W + 2);
-    emu_build_table(c, tab.data() + 1, ts.kmin, ts.W);
+    emu_build_table(c, tab.data() + 1, ts.kmin, ts.W, 32);
     int lg = 0;
     while ((2 << lg) <= ts.W) ++lg;
     DrawKey key;
