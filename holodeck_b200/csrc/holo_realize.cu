@@ -1245,9 +1245,11 @@ static Plan make_plan(int64_t ncell, int F, int R, int variant) {
     p.nfg = (F + FGROUP - 1) / FGROUP;
     // The cell chunking must not depend on R (or on the realization tiling): per-chunk partial sums are
     // combined in a fixed order, so a fixed chunking makes hc2 bit-identical however the realizations
-    // are partitioned over launches / GPUs (partials cost nchunk*F*NACC*R*8 bytes: 164 MB ... 1.3 GB at R = 1000);
-    // 512 chunks x (F/4) CTAs keep 148 SMs busy even when one CTA carries all realizations.
-    int64_t nchunk = 512;
+    // are partitioned over launches / GPUs (partials cost nchunk*F*NACC*R*8 bytes: 328 MB ... 2.6 GB at R = 1000).
+    // 1024 chunks: the heaviest (chunk, frequency group) item bounds the kernel from below -- 9.2 ms of a 10.3 ms
+    // launch with 512 chunks at R = 1000, and MORE than the balanced time at R = 100 (4.2 vs 3.2 ms).  1024 halves
+    // it (R = 100: 4.3 -> 3.5 ms); 2048 gains nothing more and costs partial-sum traffic at R = 1000.
+    int64_t nchunk = 1024;
     int64_t chunk = (ncell + nchunk - 1) / nchunk;
     chunk = ((chunk + 63) / 64) * 64;
     if (chunk < 64) chunk = 64;

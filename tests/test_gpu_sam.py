@@ -257,8 +257,19 @@ def test_full_size_named_config_properties(holo):
     tot = (hc_bg**2 + np.sum(hc_ss**2, axis=-1))
     mean_exp = (number * h2fdf).sum(dim=(0, 1, 2)).cpu().numpy()
     var_exp = (number * h2fdf * h2fdf).sum(dim=(0, 1, 2)).cpu().numpy()
-    zz = (tot.mean(axis=1) - mean_exp) / np.sqrt(var_exp / R)
-    assert np.all(np.abs(zz) < 5.0), zz
+    # The sum is dominated by rare loud sources: the mean over R = 256 realizations is far from Gaussian on the upper
+    # side (skewness 5 ... 200 across the band; with other seeds single frequencies sit at +5 ... +8 "sigma"), so the
+    # acceptance region is Bernstein's inequality for a compound-Poisson sum with per-event size <= hmax, at
+    # p = 1e-9 per frequency:  |mean - mu| <= b + sqrt(b^2 + 2 ln(1/p) var / R),  b = ln(1/p) hmax / (3 R)
+    # (lower side: sub-Gaussian, b = 0).
+    hmax = torch.where(number > 0, h2fdf, torch.zeros_like(h2fdf)).amax(dim=(0, 1, 2)).cpu().numpy()
+    lnp = np.log(1e9)
+    dev = tot.mean(axis=1) - mean_exp
+    bb = lnp * hmax / (3.0 * R)
+    assert np.all(dev <= bb + np.sqrt(bb * bb + 2.0 * lnp * var_exp / R)), dev / np.sqrt(var_exp / R)
+    assert np.all(dev >= -np.sqrt(2.0 * lnp * var_exp / R)), dev / np.sqrt(var_exp / R)
+    # ... and the typical deviation is of the order of one standard error (the median is robust against the tail)
+    assert np.median(np.abs(dev) / np.sqrt(var_exp / R)) < 1.5
     assert np.all(np.diff(hc_ss[0], axis=-1) <= 0)          # slots follow the rank order at f0
     # the union of two half-runs with global realization offsets is the full run, bit for bit
     lo = sam.gwb(fobs_edges, hard, realize=R // 2, loudest=L, seed=77, r0=0)
