@@ -361,6 +361,16 @@ def run_b200(args):
         step_scatter()
     ms_scatter, _, _, _ = timed(step_scatter, args.steps)
 
+    # ---- one librarian sample (BASELINE configs[4] inner call, lib_tools.run_model: R=100, 5 loudest, parameters
+    #      and an independently drawn GWB -- both from one fused pass of the realization kernel), through the numpy API
+    def step_library_sample():
+        from holodeck_b200 import librarian
+        sam, hard = make_models(args)
+        return librarian.run_model(sam, hard, nreals=100, nloudest=5, params_flag=True, seed=seed + rank)
+    for _ in range(2):
+        step_library_sample()
+    ms_lib, _, _, _ = timed(step_library_sample, args.steps)
+
     # ---- per-stage device times (CUDA events on the launching stream), one extra profiled pass
     stages = stage_times(args, fobs_edges, R, L, seed, r0)
 
@@ -426,6 +436,9 @@ def run_b200(args):
         "loudest_retries": int(__import__("holodeck_b200").cyutils.STATS["loudest_retries"]),
         "mmbulge_scatter_on": {"ms_per_step": ms_scatter / args.steps, "value": world * ncell * R * args.steps / (ms_scatter * 1e-3),
                                "note": "same step with mmb_scatter_dex=0.3 (K6 on the device, once per SAM)"},
+        "library_sample": {"ms_per_sample": ms_lib / args.steps, "samples_per_s": world * args.steps / (ms_lib * 1e-3),
+                           "note": "librarian.run_model on the same grid: nreals=100, nloudest=5, params + gwb (one sample "
+                                   "per rank at a time; BASELINE configs[4] shards 2000 such samples over the ranks)"},
         "roofline": roofline,
         "stages_ms": {kk: round(vv, 4) for kk, vv in stages.items()},
         "kernels": per_kernel,
