@@ -914,15 +914,16 @@ head_sum_kernel(const double* __restrict__ number, const double* __restrict__ h2
     for (int f = threadIdx.x; f < F; f += blockDim.x) bsum[(int64_t)blockIdx.x * F + f] = s_sum[f];
 }
 
-// One warp per frequency: lanes sum contiguous segments of the per-block occupancy sums, a warp scan locates the
-// segment in which the cumulative sum crosses `target`, and that lane walks its segment (fixed order).
-__global__ void head_cut_kernel(const double* __restrict__ bsum, int nblk, int F, int64_t ncell,
-                                double target, int32_t* __restrict__ kf) {
-    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (f >= F) return;
-    const int seg = (nblk + 31) / 32;
-    const int b0 = lane * seg, b1 = min(nblk, b0 + seg);
+// One CTA per frequency: threads sum contiguous segments of the per-block occupancy sums, a block scan (thread order)
+// locates the segment in which the cumulative sum crosses `target`, and that thread walks its segment (fixed order).
+constexpr int HEAD_CUT_THREADS = 256;
+__global__ void __launch_bounds__(HEAD_CUT_THREADS)
+head_cut_kernel(const double* __restrict__ bsum, int nblk, int F, int64_t ncell, double target, int32_t* __restrict__ kf) {
+    __shared__ double s_incl[HEAD_CUT_THREADS];
+    __shared__ double s_wtot[HEAD_CUT_THREADS / 32];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int seg = (nblk + HEAD_CUT_THREADS - 1) / HEAD_CUT_THREADS;
+    const int b0 = min(nblk, tid * seg), b1 = min(nblk, b0 + seg);
     double mine = 0.0;
     for (int b = b0; b < b1; ++b) mine += bsum[(int64_t)b * F + f];
     double incl = mine;
@@ -931,23 +932,26 @@ __global__ void head_cut_kernel(const double* __restrict__ bsum, int nblk, int F
         const double v = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off) incl += v;
     }
-    const bool crosses = (incl >= target) && (incl - mine < target);
-    const unsigned who = __ballot_sync(0xffffffffu, crosses);
-    int64_t k = ncell;
-    if (who != 0u) {
-        const int owner = __ffs(who) - 1;
-        if (lane == owner) {
-            double cum = incl - mine;
-            for (int b = b0; b < b1; ++b) {
-                cum += bsum[(int64_t)b * F + f];
-                if (cum >= target) { k = (int64_t)(b + 1) * HEAD_ROWS; break; }
-            }
-            if (k > ncell) k = ncell;
-            kf[f] = (int32_t)k;
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    double before = 0.0;
+    for (int w = 0; w < warp; ++w) before += s_wtot[w];
+    incl += before;
+    s_incl[tid] = incl;
+    __syncthreads();
+    const double prev = tid > 0 ? s_incl[tid - 1] : 0.0;
+    const bool crosses = (incl >= target) && (prev < target);     // at most one thread: s_incl is non-decreasing
+    if (crosses) {
+        int64_t k = (int64_t)b1 * HEAD_ROWS;
+        double cum = prev;
+        for (int b = b0; b < b1; ++b) {
+            cum += bsum[(int64_t)b * F + f];
+            if (cum >= target) { k = (int64_t)(b + 1) * HEAD_ROWS; break; }
         }
-    } else if (lane == 0) {
-        kf[f] = (int32_t)ncell;
+        if (k > ncell) k = ncell;
+        kf[f] = (int32_t)k;
     }
+    if (!__syncthreads_or(crosses) && tid == 0) kf[f] = (int32_t)ncell;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1503,7 +1507,7 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     head_sum_kernel<<<nblk, 256, sizeof(double) * F, st>>>(
         g->number, g->h2fdf, g->order, ncell, F, (double)(int64_t)g->normal_threshold,
         v == V_LOUD_PAR_REDZ ? 1 : 0, g->counts ? 1 : 0, l.bsum); holo::count_launches(1);
-    head_cut_kernel<<<(F + 3) / 4, 128, 0, st>>>(l.bsum, nblk, F, ncell, (double)L + margin, l.kf); holo::count_launches(1);
+    head_cut_kernel<<<F, HEAD_CUT_THREADS, 0, st>>>(l.bsum, nblk, F, ncell, (double)L + margin, l.kf); holo::count_launches(1);
     int rc = holo_check_launch("holo_loudest: head preparation");
     if (rc) return rc;
 
