@@ -136,6 +136,47 @@ def cosmo_params(cosmo):
     return cp
 
 
+DC_TABLE_N = 2048          # intervals of the comoving-distance table
+DC_TABLE_ZMAX = 20.0       # beyond it the kernels fall back to the quadrature
+_DC_TABLES = {}
+
+
+def dc_table_host(om0, n=DC_TABLE_N, zmax=DC_TABLE_ZMAX):
+    """Nodes ``(R_i, h R'_i)`` of ``R(w) = (1/w) int_{1-w}^{1} g(s) ds``, ``g = 2 / sqrt(Om0 + (1-Om0) s^6)``, at
+    ``w_i = i h`` (``include/holo_b200.h``, `dc_table`): flat LCDM without radiation, the same integrand as
+    ``cosmology.comoving_distance`` (``gravwaves.py:718`` via astropy/cosmopy in the reference).  The node integrals are
+    running sums of 16-point Gauss-Legendre panels, one per interval (error << 1e-15)."""
+    from .cosmology import _GL_X, _GL_W
+    ol = 1.0 - om0
+    wmax = 1.0 - 1.0 / math.sqrt(1.0 + zmax)
+    hh = wmax / n
+
+    def gg(ss):
+        return 2.0 / np.sqrt(om0 + ol * ss**6)
+    wn = np.arange(n + 1) * hh
+    mid = 0.5 * (wn[1:] + wn[:-1])
+    vv = mid[:, None] + 0.5 * hh * np.asarray(_GL_X)[None, :]
+    panels = 0.5 * hh * np.sum(np.asarray(_GL_W)[None, :] * gg(1.0 - vv), axis=1)
+    ff = np.concatenate([[0.0], np.cumsum(panels)])
+    rr = np.empty(n + 1)
+    rp = np.empty(n + 1)
+    rr[1:] = ff[1:] / wn[1:]
+    rr[0] = gg(1.0)
+    rp[1:] = (gg(1.0 - wn[1:]) - rr[1:]) / wn[1:]
+    rp[0] = 3.0 * ol                               # R'(0) = -g'(1)/2,  g'(s) = -6 OL s^5 (Om0 + OL s^6)^(-3/2)
+    return np.ascontiguousarray(np.stack([rr, hh * rp], axis=1)), n, wmax
+
+
+def dc_table(cosmo):
+    """The table on the current device, built once per (Om0, device)."""
+    import torch
+    key = (float(cosmo.Om0), torch.cuda.current_device())
+    if key not in _DC_TABLES:
+        tab, n, wmax = dc_table_host(float(cosmo.Om0))
+        _DC_TABLES[key] = (to_dev(tab), n, wmax)
+    return _DC_TABLES[key]
+
+
 _P = C.c_void_p
 _D = C.c_double
 _I = C.c_int
@@ -160,9 +201,9 @@ SIGNATURES = {
     "holo_dbn_gw": [CyConsts, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P],
     "holo_integrate_differential_number_3dx1d": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "holo_char_strain_sq": [C.POINTER(CosmoParams), _D, _D, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I,
-                            _P, _P, _P, _P, _P, _P, _P],
+                            _P, _P, _P, _P, _P, _P, _P, _I, _D, _P],
     "holo_integrate_and_strain": [C.POINTER(CosmoParams), _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                                  _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+                                  _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _D, _P],
     "holo_gwb_expectation": [_P, _P, _L, _I, _P, _P],
     "holo_sam_poisson_gwb": [_P, _P, _L, _I, _I, _L, _U, _D, _P, _P, _P, _L, _P],
     "holo_loudest_workspace_bytes": [_I, _L, _I, _I, _I, _I],

@@ -171,4 +171,22 @@ HOLO_HD double comoving_distance_cm(const GLTable& gl, double hubble_distance, d
     return hubble_distance * half * tot;
 }
 
+// The same distance from a table (optional, built by the host once per cosmology: holodeck_b200/_lib.py:dc_table):
+// with w = 1 - (1+z)^(-1/2), d_c = hubble_distance * w * R(w), R(w) = (1/w) int_{1-w}^{1} 2 ds / sqrt(Om0 + OL s^6), a
+// smooth O(1) function tabulated at n+1 uniform nodes in w as pairs (R_i, h R'_i) and evaluated by cubic Hermite
+// interpolation (relative error 2e-15 at n = 2048, uniformly down to z -> 0 because R, not d_c, is interpolated).
+// One sqrt, one division and two 16 B loads instead of 16 sqrt + 16 divisions.  Returns < 0 outside the table.
+HOLO_HD double comoving_distance_table(const double* tab, int n, double inv_h, double hubble_distance, double zz) {
+    const double sq = sqrt(1.0 + zz);
+    const double w = zz / (sq * (sq + 1.0));
+    const double u = w * inv_h;
+    const int i = (int)u;
+    if (!(u >= 0.0) || i >= n) return -1.0;
+    const double t = u - (double)i;
+    const double r0 = tab[2 * i], d0 = tab[2 * i + 1], r1 = tab[2 * i + 2], d1 = tab[2 * i + 3];
+    const double omt = 1.0 - t, t2 = t * t, o2 = omt * omt;
+    const double rr = ((1.0 + 2.0 * t) * o2) * r0 + (t * o2) * d0 + (t2 * (3.0 - 2.0 * t)) * r1 - (t2 * omt) * d1;
+    return hubble_distance * w * rr;
+}
+
 }  // namespace holo

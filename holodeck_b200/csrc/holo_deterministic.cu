@@ -303,7 +303,8 @@ bin_kernel(BinGeom g, GLTable gl, double hubble_distance, double om0, double gw_
            const double* __restrict__ mr_mid, const double* __restrict__ fc,
            const double* __restrict__ fc_over_df, double* __restrict__ numb,
            double* __restrict__ h2fdf, double* __restrict__ zmid, double* __restrict__ dcom,
-           double* __restrict__ sepa, double* __restrict__ angs, int32_t* __restrict__ bad_redz) {
+           double* __restrict__ sepa, double* __restrict__ angs, int32_t* __restrict__ bad_redz,
+           const double* __restrict__ dc_tab, int dc_n, double dc_inv_h) {
     const int Qb = g.Q - 1, Zb = g.Z - 1, F = g.F;
     const int mm = blockIdx.x / Qb, qq = blockIdx.x - mm * Qb;
     bool any_bad = false;
@@ -334,7 +335,7 @@ bin_kernel(BinGeom g, GLTable gl, double hubble_distance, double om0, double gw_
             const double zc = redz_final ? corner_mean_redz(redz_final, sM, sQ, sZ, base, bad_redz ? &bad : nullptr) : rz_mid[zz];
             any_bad |= bad;
             const StrainOut o = strain_cell(gl, hubble_distance, om0, gw_src_const, nwtg, zc, mc, mtm, fc[ff],
-                                            fc_over_df[ff], want_par);
+                                            fc_over_df[ff], want_par, dc_tab, dc_n, dc_inv_h);
             h2fdf[i] = o.h2fdf;
             if (zmid) zmid[i] = o.zmid;
             if (dcom) dcom[i] = o.dcom;
@@ -582,7 +583,7 @@ int holo_integrate_differential_number_3dx1d(const double* log10_mtot, const dou
     GLTable gl{};
     bin_kernel<true, false><<<(M - 1) * (Q - 1), 256, 0, (cudaStream_t)stream>>>(
         g, gl, 0, 0, 0, 0, log10_mtot, mrat, redz, dln_freq, dnum, nullptr, nullptr, nullptr, nullptr,
-        nullptr, nullptr, numb, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr); holo::count_launches(1);
+        nullptr, nullptr, numb, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0.0); holo::count_launches(1);
     return holo_check_launch("holo_integrate_differential_number_3dx1d");
 }
 
@@ -596,7 +597,9 @@ int holo_char_strain_sq(const holo_cosmo_params* cosmo, double gw_src_const, dou
                         const double* redz_final, const double* rz_mid, const double* mt_mid,
                         const double* mr_mid, const double* fc, const double* fc_over_df, int M,
                         int Q, int Z, int F, double* h2fdf, double* zmid, double* dcom, double* sepa,
-                        double* angs, int32_t* bad_redz, void* stream) {
+                        double* angs, int32_t* bad_redz, const double* dc_table, int dc_n, double dc_wmax,
+                        void* stream) {
+    HOLO_REQUIRE(dc_table == nullptr || (dc_n > 0 && dc_wmax > 0.0), "holo_char_strain_sq: bad distance table");
     HOLO_REQUIRE(cosmo && (redz_final || rz_mid) && mt_mid && mr_mid && fc && fc_over_df && h2fdf,
                  "holo_char_strain_sq: NULL argument");
     HOLO_REQUIRE(M > 1 && Q > 1 && Z > 1 && F > 0, "holo_char_strain_sq: bad shape");
@@ -605,7 +608,7 @@ int holo_char_strain_sq(const holo_cosmo_params* cosmo, double gw_src_const, dou
     bin_kernel<false, true><<<(M - 1) * (Q - 1), 256, 0, st>>>(
         g, to_gl(cosmo), cosmo->hubble_distance, cosmo->om0, gw_src_const, nwtg, nullptr, nullptr,
         nullptr, nullptr, nullptr, redz_final, rz_mid, mt_mid, mr_mid, fc, fc_over_df, nullptr, h2fdf,
-        zmid, dcom, sepa, angs, bad_redz); holo::count_launches(1);
+        zmid, dcom, sepa, angs, bad_redz, dc_table, dc_n, dc_table ? dc_n / dc_wmax : 0.0); holo::count_launches(1);
     return holo_check_launch("holo_char_strain_sq");
 }
 
@@ -615,7 +618,8 @@ int holo_integrate_and_strain(const holo_cosmo_params* cosmo, double gw_src_cons
                               const double* mt_mid, const double* mr_mid, const double* fc,
                               const double* fc_over_df, int M, int Q, int Z, int F, double* numb,
                               double* h2fdf, double* zmid, double* dcom, double* sepa, double* angs,
-                              int32_t* bad_redz, void* stream) {
+                              int32_t* bad_redz, const double* dc_table, int dc_n, double dc_wmax, void* stream) {
+    HOLO_REQUIRE(dc_table == nullptr || (dc_n > 0 && dc_wmax > 0.0), "holo_integrate_and_strain: bad distance table");
     HOLO_REQUIRE(cosmo && log10_mtot && mrat && redz && dln_freq && dnum && redz_final && mt_mid &&
                  mr_mid && fc && fc_over_df && numb && h2fdf, "holo_integrate_and_strain: NULL argument");
     HOLO_REQUIRE(M > 1 && Q > 1 && Z > 1 && F > 0, "holo_integrate_and_strain: bad shape");
@@ -624,7 +628,7 @@ int holo_integrate_and_strain(const holo_cosmo_params* cosmo, double gw_src_cons
     bin_kernel<true, true><<<(M - 1) * (Q - 1), 256, 0, st>>>(
         g, to_gl(cosmo), cosmo->hubble_distance, cosmo->om0, gw_src_const, nwtg, log10_mtot, mrat, redz,
         dln_freq, dnum, redz_final, nullptr, mt_mid, mr_mid, fc, fc_over_df, numb, h2fdf, zmid, dcom,
-        sepa, angs, bad_redz); holo::count_launches(1);
+        sepa, angs, bad_redz, dc_table, dc_n, dc_table ? dc_n / dc_wmax : 0.0); holo::count_launches(1);
     return holo_check_launch("holo_integrate_and_strain");
 }
 

@@ -387,11 +387,16 @@ struct StrainOut {
 
 HOLO_HD StrainOut strain_cell(const GLTable& gl, double hubble_distance, double om0,
                               double gw_src_const, double nwtg, double zc, double mc, double mt_mid,
-                              double fc, double fc_over_df, bool want_params) {
+                              double fc, double fc_over_df, bool want_params, const double* dc_tab = nullptr,
+                              int dc_n = 0, double dc_inv_h = 0.0) {
     StrainOut o;
     const double inf = 1.0 / 0.0;
     const bool sel = (zc > 0.0);
-    const double dc = sel ? comoving_distance_cm(gl, hubble_distance, om0, zc) : inf;
+    double dc = inf;
+    if (sel) {
+        dc = dc_tab ? comoving_distance_table(dc_tab, dc_n, dc_inv_h, hubble_distance, zc) : -1.0;
+        if (dc < 0.0) dc = comoving_distance_cm(gl, hubble_distance, om0, zc);      // no table, or beyond it
+    }
     double h2 = 0.0;
     if (sel) {
         const double fr = fc * (1.0 + zc);                               // utils.frst_from_fobs

@@ -56,6 +56,7 @@ def _char_strain_sq(edges, redz, params=False, device=False, dnum=None):
         redz_d = _lib.to_dev(redz)
         assert tuple(redz_d.shape) == (M, Q, Z, F), f"`redz` shape {tuple(redz_d.shape)} != {(M, Q, Z, F)}"
     cp = _lib.cosmo_params(cosmo)
+    dc_tab, dc_n, dc_wmax = _lib.dc_table(cosmo)
     mt_d, mr_d, rz_d, fc_d, fdf_d = [_lib.to_dev(vv) for vv in (mt, mr, rz, fc, fdf)]
     import torch
     out = dict(h2fdf=_lib.empty(shape))
@@ -68,7 +69,7 @@ def _char_strain_sq(edges, redz, params=False, device=False, dnum=None):
         rc = lib.holo_char_strain_sq(
             C.byref(cp), utils._GW_SRC_CONST, NWTG, _lib.ptr(redz_d), _lib.ptr(rz_d), _lib.ptr(mt_d), _lib.ptr(mr_d),
             _lib.ptr(fc_d), _lib.ptr(fdf_d), M, Q, Z, F, _lib.ptr(out["h2fdf"]),
-            *[_lib.ptr(out[nn]) for nn in names], _lib.ptr(out["bad_redz"]), _lib.stream())
+            *[_lib.ptr(out[nn]) for nn in names], _lib.ptr(out["bad_redz"]), _lib.ptr(dc_tab), dc_n, dc_wmax, _lib.stream())
         _lib.check(rc, "char_strain_sq")
     else:
         dnum_d = _lib.to_dev(dnum)
@@ -80,7 +81,7 @@ def _char_strain_sq(edges, redz, params=False, device=False, dnum=None):
             C.byref(cp), utils._GW_SRC_CONST, NWTG, _lib.ptr(l10m), _lib.ptr(mrat_d), _lib.ptr(redz_e), _lib.ptr(dlnf),
             _lib.ptr(dnum_d), _lib.ptr(redz_d), _lib.ptr(mt_d), _lib.ptr(mr_d), _lib.ptr(fc_d), _lib.ptr(fdf_d),
             M, Q, Z, F, _lib.ptr(out["number"]), _lib.ptr(out["h2fdf"]),
-            *[_lib.ptr(out[nn]) for nn in names], _lib.ptr(out["bad_redz"]), _lib.stream())
+            *[_lib.ptr(out[nn]) for nn in names], _lib.ptr(out["bad_redz"]), _lib.ptr(dc_tab), dc_n, dc_wmax, _lib.stream())
         _lib.check(rc, "integrate_and_strain")
     return out
 

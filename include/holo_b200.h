@@ -174,6 +174,10 @@ int holo_integrate_differential_number_3dx1d(const double* log10_mtot, const dou
  *  `gw_src_const`/`nwtg` are the astropy-valued constants of utils.py:40 / constants.py:23.
  *  If `redz_final` is NULL, `rz_mid` (Z-1,) is used for all cells: char_strain_sq_from_bin_edges,
  *  gravwaves.py:760-783.
+ *  `dc_table` (optional, device): the comoving distance as a table instead of a 16-point quadrature per cell:
+ *  2 (dc_n + 1) doubles, pairs (R_i, h R'_i) at the uniform nodes w_i = i dc_wmax / dc_n of
+ *  R(w) = (1/w) int_{1-w}^{1} 2 ds / sqrt(Om0 + (1-Om0) s^6),  w = 1 - (1+z)^(-1/2),  d_c = hubble_distance w R(w)
+ *  (cubic Hermite; the quadrature remains the fallback beyond the table).
  *  `bad_redz` (optional, one zero-initialised int32 on the device) is set to 1 when some redz_final value is
  *  negative but not the -1 sentinel -- the input check of single_sources.py:95-99, made while the values are
  *  being read instead of in separate passes over the grid.
@@ -182,7 +186,8 @@ int holo_char_strain_sq(const holo_cosmo_params* cosmo_host, double gw_src_const
                         const double* redz_final, const double* rz_mid, const double* mt_mid,
                         const double* mr_mid, const double* fc, const double* fc_over_df, int M,
                         int Q, int Z, int F, double* h2fdf, double* zmid, double* dcom, double* sepa,
-                        double* angs, int32_t* bad_redz, void* stream);
+                        double* angs, int32_t* bad_redz, const double* dc_table, int dc_n, double dc_wmax,
+                        void* stream);
 
 /* Fused K2 + K2b for the sam.gwb pipeline: one pass over (diff_num, redz_final) producing
  * (number, h2fdf [, zmid, dcom, sepa, angs]). */
@@ -192,7 +197,8 @@ int holo_integrate_and_strain(const holo_cosmo_params* cosmo_host, double gw_src
                               const double* mt_mid, const double* mr_mid, const double* fc,
                               const double* fc_over_df, int M, int Q, int Z, int F, double* numb,
                               double* h2fdf, double* zmid, double* dcom, double* sepa, double* angs,
-                              int32_t* bad_redz, void* stream);
+                              int32_t* bad_redz, const double* dc_table, int dc_n, double dc_wmax,
+                              void* stream);
 
 /* hc2[f] = sum_{m,q,z} number * h2fdf   (realize=False branch, gravwaves.py:481-485, 557-561) */
 int holo_gwb_expectation(const double* number, const double* h2fdf, int64_t ncell, int F,

@@ -157,3 +157,27 @@ def test_library_combine_contract(tmp_path):
     (sims / "library__p000004.npz").unlink()
     with pytest.raises(ValueError):
         combine.sam_lib_combine(tmp_path, holo.log, recreate=True)
+
+
+def test_comoving_distance_table_against_independent_quadrature():
+    """The Hermite table the strain kernel reads (`_lib.dc_table_host`, include/holo_b200.h `dc_table`) against the
+    oracle's adaptive quadrature: the reference takes d_c from astropy/cosmopy (gravwaves.py:718); 1e-13 here."""
+    from holodeck_b200 import _lib, cosmo
+    from oracle import glue
+    tab, n, wmax = _lib.dc_table_host(float(cosmo.Om0))
+    assert tab.shape == (n + 1, 2) and 10.0 < (1.0 / (1.0 - wmax))**2 - 1.0 <= 20.0 + 1e-9
+    hh = wmax / n
+    rng = np.random.default_rng(3)
+    zs = np.concatenate([10**rng.uniform(-6, np.log10(19.9), 300), [1e-3, 10.0]])
+    sq = np.sqrt(1 + zs)
+    ww = zs / (sq * (sq + 1))
+    uu = ww / hh
+    ii = uu.astype(int)
+    tt = uu - ii
+    r0, d0, r1, d1 = tab[ii, 0], tab[ii, 1], tab[ii + 1, 0], tab[ii + 1, 1]
+    omt = 1 - tt
+    rr = ((1 + 2*tt) * omt * omt) * r0 + (tt * omt * omt) * d0 + (tt * tt * (3 - 2*tt)) * r1 - (tt * tt * omt) * d1
+    got = cosmo.hubble_distance * ww * rr
+    oc = glue.OracleCosmo()
+    want = np.array([oc.comoving_distance(zz) for zz in zs])
+    assert np.max(np.abs(got / want - 1.0)) < 1e-13
