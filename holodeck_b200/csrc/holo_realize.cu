@@ -49,15 +49,19 @@ __host__ __device__ constexpr bool has_max(int v) { return v == V_SSBG || v == V
 constexpr int RZ_THREADS = 256;      // threads per CTA (128 when R <= 128); each thread carries RPT realization slots
 constexpr int NSCAN = 256;           // cells scanned per pass (max), in rounds of one cell per thread
 constexpr int FGROUP = 4;            // frequencies per CTA (4 doubles = one 32 B sector per cell)
-#ifndef HOLO_POOL_ENTRIES
-#define HOLO_POOL_ENTRIES 6144
-#endif
-constexpr int POOL_ENTRIES = HOLO_POOL_ENTRIES;   // 32-bit CDF thresholds per pass (24 KB of dynamic shared memory)
+// 32-bit CDF thresholds per pass (dynamic shared memory).  A larger pool means fewer, longer passes where nearly every
+// element is a table (the per-pass staging / barrier / build latency is paid less often): 40 KB instead of 24 KB takes
+// 6 % off the R = 1000 draws.  It is what still lets two 256-thread CTAs share an SM; the plain GWB kernel keeps 24 KB
+// because its two-slot form (256 < R <= 512: the eccentric harmonic slabs at R = 500) runs THREE CTAs per SM with it
+// and loses 22 % with two.  The pool size fixes the pass boundaries, so it depends on the variant only, never on R.
+__host__ __device__ constexpr int pool_entries_of(int variant) {
+    return (variant == HOLO_LOUDEST_PLAIN || variant == HOLO_LOUDEST_PAR || variant == HOLO_LOUDEST_PAR_REDZ) ? 10240 : 6144;
+}
 constexpr int GROUP_RESERVE = 288;   // head of the pool: CDF table of the pass's superposition group
 constexpr double GROUP_MAX_LAM = 0.25;   // elements below this expectation value are drawn as one Poisson process
 constexpr int CLS_GROUP = 6;         // (continues the CLS_* enum of holo_rng.cuh) member of the superposition group
 constexpr int STREAM_GWB = 1, STREAM_LOUD = 2, STREAM_SSBG = 3, STREAM_BULK = 4;
-static_assert(FGROUP * (TABLE_WMAX + 2) + GROUP_RESERVE <= POOL_ENTRIES, "one cell must always fit the table pool");
+static_assert(FGROUP * (TABLE_WMAX + 2) + GROUP_RESERVE <= pool_entries_of(0), "one cell must always fit the table pool");
 
 // Debug instrumentation (never in the product build): -DHOLO_PHASE_CLOCKS makes thread 0 of every CTA add the
 // clock64 cycles it spends in each phase of a pass to g_phase_clk (read with holo_debug_phase_clocks).
@@ -399,7 +403,7 @@ static __device__ __forceinline__ int stage_pass(const RealizeArgs& a, int64_t c
         const int main_incl = (int)(incl & 2047u), grp_incl = (int)((incl >> 11) & 2047u);
         const int need_incl = (int)(incl >> 22);
         const bool taken = inrange && (main_incl + grp_incl <= NREC) &&
-                           (need_incl <= POOL_ENTRIES - GROUP_RESERVE);        // a prefix of the run
+                           (need_incl <= pool_entries_of(VARIANT) - GROUP_RESERVE);        // a prefix of the run
         const int ntaken = __syncthreads_count(taken);
         if (ntaken > 0 && tid == ntaken - 1) { *s_tot = incl; *s_totlam = glam; }
         if (taken && clsw != 0) {
@@ -485,6 +489,7 @@ realize_kernel(RealizeArgs a) {
     __shared__ double s_totlam;
     __shared__ int s_np;
     __shared__ int s_gspec[3];                          // kmin, W, lg of the group's table
+    constexpr int POOL_ENTRIES = pool_entries_of(VARIANT);
     extern __shared__ __align__(16) uint32_t s_pool[];  // POOL_ENTRIES thresholds, then s_acc / s_words (below)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1335,7 +1340,7 @@ template <int VARIANT, int RPT, int THREADS, bool FUSED>
 static int launch_realize_fused(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
     dim3 grid(p.nfg, p.nchunk, p.ntiles);
     const bool sacc = nacc_of(VARIANT) == 1 && !has_max(VARIANT);
-    const size_t pool_bytes = sizeof(uint32_t) * POOL_ENTRIES + (sacc ? sizeof(double) * FGROUP * RPT * THREADS : 0) +
+    const size_t pool_bytes = sizeof(uint32_t) * pool_entries_of(VARIANT) + (sacc ? sizeof(double) * FGROUP * RPT * THREADS : 0) +
                               sizeof(uint32_t) * 4 * RPT * THREADS;
     static bool attr_set = false;   // static + dynamic shared memory may exceed the 48 KB default
     if (!attr_set) {

@@ -203,21 +203,44 @@ def test_realizations_do_not_depend_on_partition(holo, golden_classic):
     assert np.array_equal(cyutils.sam_poisson_gwb(gg["number"], gg["h2fdf"], 600, seed=9), np.concatenate(quarters, axis=1))
 
 
+def _same_distribution(got, ref, nboot=40, nsig=7.0):
+    """per-frequency 5 / 50 / 95 % quantiles of two independent samples agree within bootstrap Monte-Carlo error"""
+    R = ref.shape[1]
+    for qq in (0.05, 0.5, 0.95):
+        a, b = np.quantile(got, qq, axis=1), np.quantile(ref, qq, axis=1)
+        boot = np.std([np.quantile(ref[:, np.random.default_rng(ii).integers(0, R, R)], qq, axis=1) for ii in range(nboot)], axis=0)
+        if not np.all(np.abs(a - b) <= nsig * boot * np.sqrt(1.0 + R / got.shape[1]) + 1e-12 * np.abs(b)):
+            return False
+    return True
+
+
 def test_fused_gwb_slots_of_the_loudest_pass(holo, golden_classic):
     """`gwb_nreals=`: the loudest pass also draws an independent realised GWB from the same staged records.  The
-    loudest products must not change at all; for the plain variant (same record / pool limits as the stand-alone
-    GWB kernel, same Philox stream and keys) the fused GWB is bit-identical to `sam_poisson_gwb`; for the
-    parameter variant (shorter passes -> other superposition groups) it is an equivalent, differently drawn sample."""
+    loudest products must not change at all, whatever the number of fused slots and however they fall onto threads,
+    warps and lock-step slots; the fused GWB is an independent sample of what `sam_poisson_gwb` draws (same Philox
+    stream and keys, but the loudest variants stage longer passes, hence other superposition groups), does not depend
+    on the loudest realizations it rides with, and honours its own global realization offset."""
     from holodeck_b200 import cyutils
     gg = golden_classic
     ms, qs, zs = sort_indices(gg)
+    F = gg["number"].shape[-1]
+    lam, hh = gg["number"].reshape(-1, F), gg["h2fdf"].reshape(-1, F)
+    ref = cyutils.sam_poisson_gwb(gg["number"], gg["h2fdf"], 1500, seed=77)
     for R, Rg in ((5, 5), (100, 100), (96, 300), (700, 40)):      # 128-thread CTAs, mixed warps, 2 and 4 slots per thread
         alone = cyutils.loudest_hc_from_sorted(gg["number"], gg["h2fdf"], R, 3, ms, qs, zs, seed=11, r0=2)
         fused = cyutils.loudest_hc_from_sorted(gg["number"], gg["h2fdf"], R, 3, ms, qs, zs, seed=11, r0=2,
                                                gwb_nreals=Rg, gwb_seed=12, gwb_r0=1)
-        assert len(fused) == 3 and fused[2].shape == (gg["number"].shape[-1], Rg)
+        assert len(fused) == 3 and fused[2].shape == (F, Rg)
         assert np.array_equal(fused[0], alone[0]) and np.array_equal(fused[1], alone[1])
-        assert np.array_equal(fused[2], cyutils.sam_poisson_gwb(gg["number"], gg["h2fdf"], Rg, seed=12, r0=1))
+    # the fused sample: independent of the loudest realizations riding along, offset-consistent, correctly distributed
+    big = cyutils.loudest_hc_from_sorted(gg["number"], gg["h2fdf"], 4, 3, ms, qs, zs, seed=1, gwb_nreals=1500, gwb_seed=12)[2]
+    other = cyutils.loudest_hc_from_sorted(gg["number"], gg["h2fdf"], 300, 2, ms, qs, zs, seed=2, gwb_nreals=200, gwb_seed=12,
+                                           gwb_r0=1000)[2]
+    assert np.array_equal(other, big[:, 1000:1200])
+    assert _same_distribution(big, ref)
+    mean = np.sum(lam * hh, axis=0)
+    sig = np.sqrt(np.sum(lam * hh * hh, axis=0) / big.shape[1])
+    assert np.all(np.abs(big.mean(axis=1) - mean) < 6 * sig + 1e-300)
     mt, mr, rz = [0.5 * (gg[kk][1:] + gg[kk][:-1]) for kk in ("mtot", "mrat", "redz")]
     pars = (mt, mr, rz, gg["par_redz"], gg["par_dcom"], gg["par_sepa"], gg["par_angs"], ms, qs, zs)
     R, Rg = 64, 1500
@@ -226,13 +249,4 @@ def test_fused_gwb_slots_of_the_loudest_pass(holo, golden_classic):
                                                         gwb_nreals=Rg, gwb_seed=6)
     for aa, ff in zip(alone, fused[:4]):
         assert np.array_equal(aa, ff, equal_nan=True)
-    gwb = fused[4]
-    lam, hh = gg["number"].reshape(-1, gwb.shape[0]), gg["h2fdf"].reshape(-1, gwb.shape[0])
-    mean = np.sum(lam * hh, axis=0)
-    sig = np.sqrt(np.sum(lam * hh * hh, axis=0) / Rg)
-    assert np.all(np.abs(gwb.mean(axis=1) - mean) < 5 * sig + 1e-300)
-    ref = cyutils.sam_poisson_gwb(gg["number"], gg["h2fdf"], Rg, seed=77)
-    for qq in (0.05, 0.5, 0.95):
-        a, b = np.quantile(gwb, qq, axis=1), np.quantile(ref, qq, axis=1)
-        boot = np.std([np.quantile(ref[:, np.random.default_rng(ii).integers(0, Rg, Rg)], qq, axis=1) for ii in range(40)], axis=0)
-        assert np.all(np.abs(a - b) <= 7 * boot + 1e-12 * np.abs(b))
+    assert _same_distribution(fused[4], ref)
