@@ -17,6 +17,7 @@ N > 1             realizations shard: every rank runs R realizations (global rea
                   oracle/chain.py), all host cores, on a bounded sample of the same workload.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -45,6 +46,7 @@ def parse_args():
     ap.add_argument("--nfreqs", type=int, default=40)
     ap.add_argument("--realize", type=int, default=1000)
     ap.add_argument("--loudest", type=int, default=1, help="sam.gwb default")
+    ap.add_argument("--settle-steps", type=int, default=60, help="untimed steps after the W warm-up steps (clock/allocator settle)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-reals", type=int, default=2, help="realizations in the bounded CPU sample")
     return ap.parse_args()
@@ -312,29 +314,51 @@ def run_b200(args):
 
     def timed(fn, nsteps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # a full (generation 2) pass of Python's cycle collector over the torch/numpy/scipy heap takes 30-60 ms --
+        # several steps -- and lands wherever the allocation counter says: collect now, keep the collector off for
+        # the K timed steps (device buffers are freed by reference counting, not by the collector)
+        gc.collect()
+        gc.disable()
         barrier()
         t0 = time.perf_counter()
         ev0.record()
+        marks = [ev0]
         for _ in range(nsteps):
             out = fn()
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         ev1.record()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        gc.enable()
         barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # per-step spread on this rank (diagnostic only: the reported time is the bracket above)
+        timed.last_steps = [marks[ii].elapsed_time(marks[ii + 1]) for ii in range(nsteps)]
         return float(ms.item()), out, t0, t1
 
     # the clock sampler (nvidia-smi) is started BEFORE the warm-up: its NVML start-up stalls kernel
     # submission for tens of ms and must not land in the timed region
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("HOLO_BENCH_NO_SAMPLER"):
         sampler.start()
     for _ in range(args.warmup):
         step_device()
+    # a fresh box needs more than W x 13 ms to leave its idle power state and settle the caching allocator: a fixed
+    # number of further untimed steps (the same on every rank: each step ends in a collective) on top of the W
+    # requested ones, about a second of device work
+    extra_warmup = max(0, args.settle_steps)
+    for _ in range(extra_warmup):
+        step_device()
+    torch.cuda.synchronize()
     n_launch0 = lib.holo_launch_count()
     ms_total, out, t0, t1 = timed(step_device, args.steps)
+    slowest = int(np.argmax(timed.last_steps))
+    if os.environ.get("HOLO_BENCH_DUMP_STEPS"):
+        print("step_ms", [round(xx, 2) for xx in timed.last_steps], file=sys.stderr)
+    steps_ms = sorted(timed.last_steps)
     n_launch = lib.holo_launch_count() - n_launch0
     value = world * ncell * R * args.steps / (ms_total * 1e-3)
 
@@ -430,6 +454,10 @@ def run_b200(args):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args),
         "clocks": clocks,
+        "step_ms_spread": {"min": round(steps_ms[0], 3), "median": round(steps_ms[len(steps_ms) // 2], 3),
+                           "max": round(steps_ms[-1], 3), "slowest_step": slowest, "extra_warmup_steps": extra_warmup,
+                           "note": "per-step CUDA-event times of the timed region on rank 0 (diagnostic; `ms_per_step` is the "
+                                   "bracket over all K steps); extra untimed warm-up steps run after the W requested ones"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(n_launch),
