@@ -344,15 +344,15 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0 and not os.environ.get("HOLO_BENCH_NO_SAMPLER"):
         sampler.start()
-    for _ in range(args.warmup):
-        step_device()
-    # a fresh box needs more than W x 13 ms to leave its idle power state and settle the caching allocator: a fixed
-    # number of further untimed steps (the same on every rank: each step ends in a collective) on top of the W
-    # requested ones, about a second of device work
+    # Warm-up runs through the SAME bracket as the timed region (same events, same lifetime of the previous step's
+    # outputs, hence the same caching-allocator pattern): on a fresh box the first process otherwise paid a one-off
+    # 35-100 ms stall in the 4th timed step (a first-time segment allocation while the NVML child polls the driver).
+    # After the W requested steps a fixed number of further untimed steps (the same on every rank: each step ends in
+    # a collective), about a second of device work, lets clocks and allocator settle.
+    timed(step_device, max(1, args.warmup))
     extra_warmup = max(0, args.settle_steps)
-    for _ in range(extra_warmup):
-        step_device()
-    torch.cuda.synchronize()
+    if extra_warmup:
+        timed(step_device, extra_warmup)
     n_launch0 = lib.holo_launch_count()
     ms_total, out, t0, t1 = timed(step_device, args.steps)
     slowest = int(np.argmax(timed.last_steps))
@@ -363,8 +363,7 @@ def run_b200(args):
     value = world * ncell * R * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the public numpy API
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
+    timed(step_e2e, max(2, min(args.warmup, 4)))
     _lib.TRAFFIC["h2d"] = _lib.TRAFFIC["d2h"] = 0
     ms_e2e, out_e2e, _, _ = timed(step_e2e, args.steps)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
@@ -381,8 +380,7 @@ def run_b200(args):
         sam, hard = make_models(args, scatter_dex=0.3)
         hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0, device=True)
         return gather(hc_ss), gather(hc_bg)
-    for _ in range(2):
-        step_scatter()
+    timed(step_scatter, 4)
     ms_scatter, _, _, _ = timed(step_scatter, args.steps)
 
     # ---- one librarian sample (BASELINE configs[4] inner call, lib_tools.run_model: R=100, 5 loudest, parameters
@@ -391,8 +389,7 @@ def run_b200(args):
         from holodeck_b200 import librarian
         sam, hard = make_models(args)
         return librarian.run_model(sam, hard, nreals=100, nloudest=5, params_flag=True, seed=seed + rank)
-    for _ in range(2):
-        step_library_sample()
+    timed(step_library_sample, 4)
     ms_lib, _, _, _ = timed(step_library_sample, args.steps)
 
     # ---- per-stage device times (CUDA events on the launching stream), one extra profiled pass
