@@ -234,7 +234,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": round(wall, 1),
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -478,7 +478,7 @@ def run_b200(args):
                 **info}
         except Exception as err:   # the oracle did not travel: say so instead of inventing a number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {err}"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -530,8 +530,27 @@ def stage_times(args, fobs_edges, R, L, seed, r0):
     return res
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep the real stdout for the ONE JSON line: every other writer to fd 1 -- NCCL's version banner (printed by
+    the C library under torchrun, NCCL_DEBUG_FILE notwithstanding), child processes -- lands on stderr instead."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
