@@ -93,3 +93,10 @@ def barrier():
     if is_distributed():
         import torch.distributed as dist
         dist.barrier()
+
+
+def finalize():
+    """Tear the process group down (end of ``gen_lib.main``); a no-op for a single-process run."""
+    if is_distributed():
+        import torch.distributed as dist
+        dist.destroy_process_group()

@@ -113,6 +113,7 @@ def main():
                               pta_dur=args.pta_dur, gwb_flag=args.gwb_flag, ss_flag=args.ss_flag,
                               params_flag=args.params_flag, recreate=args.recreate, seed=args.seed)
     print(f"rank {dist.world()[0]}: {done} samples, {fails} failures")
+    dist.finalize()
 
 
 if __name__ == "__main__":

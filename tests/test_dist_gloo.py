@@ -29,6 +29,9 @@ WORKER = textwrap.dedent("""
     allidx = sorted(int(v) for t in both for v in t if v >= 0)
     assert allidx == list(range(11)), allidx
     dist.barrier()
+    dist.finalize()
+    assert not dist.is_distributed()
+    dist.finalize()          # idempotent; a no-op without a process group
     print("ok", rank)
 """)
 
