@@ -227,7 +227,7 @@ def run_reference(args):
               f"deterministic stages (density, 2PL norm, dbn, integrate, strain+argsort) timed once: {info['t_deterministic_s']} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * ncell * args.realize / value,   # one step of the workload on all host cores "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * ncell * args.realize / value, "higher_is_better": True,   # ms: one step on all host cores
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample, **info},
