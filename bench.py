@@ -265,6 +265,33 @@ def make_models(args, scatter_dex=0.0):
     return sam, hard
 
 
+def deterministic_parity(sam, hard, fobs_edges, state):
+    """Parity of the very arrays a timed step produces (the product's own density, Brent roots, cosmology tables,
+    K1b, K2+K2b) against the oracle chain's `state` (oracle/chain.reference_deterministic) on the same workload:
+    per array the zero/sentinel-pattern mismatch count, the max relative error and the number of elements above
+    1e-10.  Used by the `parity` key of the JSON line and by tests/test_gpu_fullsize.py."""
+    from holodeck_b200 import _lib
+
+    def cmp(got, want, tol=1e-10):
+        got = np.asarray(got, dtype=float)
+        sel = (want != 0) & np.isfinite(want)
+        err = np.abs(got[sel] - want[sel]) / np.abs(want[sel])
+        return {"n": int(want.size), "zero_mismatch": int(np.count_nonzero((got == 0) != (want == 0))),
+                "max_rel": float(err.max()) if err.size else 0.0, f"n_above_{tol:g}": int(np.count_nonzero(err > tol))}
+
+    edges, redz_final, strain = sam._number_and_strain(fobs_edges, hard, params=False)
+    rep = {"dens": cmp(sam.static_binary_density, state["dens"])}
+    dl = np.abs(np.log10(hard._norm) - state["norm_log10"])
+    rep["norm_log10"] = {"n": int(dl.size), "max_abs": float(dl.max()), "n_above_1e-10": int(np.count_nonzero(dl > 1e-10))}
+    rz = _lib.to_host(redz_final)
+    rep["redz_final"] = cmp(rz, state["redz_final"])
+    rep["redz_final"]["sentinel_mismatch"] = int(np.count_nonzero((rz == -1.0) != (state["redz_final"] == -1.0)))
+    del rz
+    rep["number"] = cmp(_lib.to_host(strain["number"]), state["number"])
+    rep["h2fdf"] = cmp(_lib.to_host(strain["h2fdf"]), state["h2fdf"])
+    return rep
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist

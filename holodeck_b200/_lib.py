@@ -204,7 +204,8 @@ SIGNATURES = {
                             _P, _P, _P, _P, _P, _P, _P, _I, _D, _P],
     "holo_integrate_and_strain": [C.POINTER(CosmoParams), _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                   _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _D, _P],
-    "holo_gwb_expectation": [_P, _P, _L, _I, _P, _P],
+    "holo_gwb_expectation_workspace_bytes": [_I],
+    "holo_gwb_expectation": [_P, _P, _L, _I, _P, _P, _L, _P],
     "holo_sam_poisson_gwb": [_P, _P, _L, _I, _I, _L, _U, _D, _P, _P, _P, _L, _P],
     "holo_loudest_workspace_bytes": [_I, _L, _I, _I, _I, _I],
     "holo_loudest": [C.POINTER(LoudestArgs), _P],
@@ -227,6 +228,7 @@ _RESTYPES = {
     "holo_loudest_workspace_bytes": C.c_int64,
     "holo_realize_workspace_bytes": C.c_int64,
     "holo_eccen_workspace_bytes": C.c_int64,
+    "holo_gwb_expectation_workspace_bytes": C.c_int64,
 }
 
 _lib = None
@@ -254,7 +256,7 @@ def load(path=None):
             raise HoloNativeError(f"{path} does not export `{name}`") from err
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.holo_abi_version() != 2:
+    if lib.holo_abi_version() != 3:
         raise HoloNativeError(f"ABI mismatch: library reports version {lib.holo_abi_version()}")
     _lib = lib
     return lib

@@ -632,22 +632,25 @@ int holo_integrate_and_strain(const holo_cosmo_params* cosmo, double gw_src_cons
     return holo_check_launch("holo_integrate_and_strain");
 }
 
+int64_t holo_gwb_expectation_workspace_bytes(int F) {
+    return (int64_t)sizeof(double) * (int64_t)(148 * 4) * (F > 0 ? F : 1);
+}
+
 int holo_gwb_expectation(const double* number, const double* h2fdf, int64_t ncell, int F, double* hc2,
-                         void* stream) {
-    HOLO_REQUIRE(number && h2fdf && hc2 && ncell >= 0 && F > 0, "holo_gwb_expectation: bad argument");
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+    HOLO_REQUIRE(number && h2fdf && hc2 && workspace && ncell >= 0 && F > 0, "holo_gwb_expectation: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     int nblk = 148 * 4;
     int64_t cpb = (ncell + nblk - 1) / nblk;
     if (cpb < 1) cpb = 1;
     nblk = (int)((ncell + cpb - 1) / cpb);
     if (nblk < 1) nblk = 1;
-    double* partial = nullptr;
-    HOLO_CUDA(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)nblk * F, st));
+    // per-block partial sums live in the CALLER's workspace: the library itself never allocates device memory
+    HOLO_REQUIRE((int64_t)sizeof(double) * nblk * F <= workspace_bytes, "holo_gwb_expectation: workspace too small");
+    double* partial = static_cast<double*>(workspace);
     expect_partial_kernel<<<nblk, 32 * EXP_ROWS, 0, st>>>(number, h2fdf, ncell, F, cpb, partial); holo::count_launches(1);
     expect_final_kernel<<<(F + 63) / 64, 64, 0, st>>>(partial, nblk, F, hc2); holo::count_launches(1);
-    int rc = holo_check_launch("holo_gwb_expectation");
-    cudaFreeAsync(partial, st);
-    return rc;
+    return holo_check_launch("holo_gwb_expectation");
 }
 
 int holo_model_details_hist(const double* redz_edges, const double* redz_final, const double* number,

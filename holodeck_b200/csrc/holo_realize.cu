@@ -1342,11 +1342,15 @@ static int launch_realize_fused(const RealizeArgs& ra, const Plan& p, cudaStream
     const bool sacc = nacc_of(VARIANT) == 1 && !has_max(VARIANT);
     const size_t pool_bytes = sizeof(uint32_t) * pool_entries_of(VARIANT) + (sacc ? sizeof(double) * FGROUP * RPT * THREADS : 0) +
                               sizeof(uint32_t) * 4 * RPT * THREADS;
-    static bool attr_set = false;   // static + dynamic shared memory may exceed the 48 KB default
-    if (!attr_set) {
+    // static + dynamic shared memory may exceed the 48 KB default.  Function attributes are per DEVICE (each device has
+    // its own copy of the loaded function): remember the opt-in per device ordinal, not per process.
+    static bool attr_set[64] = {};
+    int dev = 0;
+    HOLO_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT, THREADS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
         HOLO_CUDA(cudaFuncSetAttribute(realize_kernel<VARIANT, RPT, THREADS, FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     realize_kernel<VARIANT, RPT, THREADS, FUSED><<<grid, THREADS, pool_bytes, st>>>(ra); holo::count_launches(1);
     return holo_check_launch("realize_kernel");

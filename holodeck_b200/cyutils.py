@@ -33,6 +33,26 @@ _MAX_RETRY = 5
 STATS = {"loudest_calls": 0, "loudest_retries": 0}
 
 
+#: the resolver sorts a bucket in shared memory: RES_WARPS * 2 * cap * 16 B <= 200 KB (holo_realize.cu) -> cap <= 1600
+_MAX_BUCKET_CAP = 1536
+
+
+def _retry_schedule(L, attempt):
+    """(head_margin, bucket_cap) of retry number ``attempt`` >= 1 of `holo_loudest` after HOLO_ERR_OVERFLOW.
+
+    The margin grows 4x per attempt from the library's default ``8 sqrt(L) + 24``; the bucket must hold the
+    ``L + margin`` events the head is cut for, with the same slack as the library's own choice
+    (``auto_cap``: next power of two >= 2 (L + margin) + 64).  Both stop growing where the bucket reaches the
+    resolver's shared-memory limit: from there on a retry keeps the largest head that still fits.
+    """
+    margin = (8.0 * np.sqrt(L) + 24.0) * (4.0 ** attempt)
+    margin = min(margin, max((_MAX_BUCKET_CAP - 64) / 2.0 - L, 8.0 * np.sqrt(L) + 24.0))
+    cap = 64
+    while cap < 2.0 * (L + margin) + 64.0:
+        cap *= 2
+    return float(margin), int(min(cap, _MAX_BUCKET_CAP))
+
+
 def _seed(seed):
     if seed is None:
         return int.from_bytes(os.urandom(8), "little")
@@ -174,9 +194,9 @@ def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, norm
         if rc != 3:
             break
         STATS["loudest_retries"] += 1
-        # bucket overflow / head too short (HOLO_ERR_OVERFLOW): enlarge both and redo the draws
-        margin = (8.0 * np.sqrt(L) + 24.0) * (4.0 ** (attempt + 1))
-        cap = min(2048, 256 * (2 ** (attempt + 1)))
+        # bucket overflow / head too short (HOLO_ERR_OVERFLOW): enlarge the head margin and redo the draws, with the
+        # bucket sized FROM the margin (about L + margin events are expected per bucket)
+        margin, cap = _retry_schedule(L, attempt + 1)
     _lib.check(rc, "loudest")
     del keep
     return out

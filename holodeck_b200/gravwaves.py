@@ -122,7 +122,9 @@ def _expectation(number, hc2):
     lib = _lib.require_gpu()
     F = number.shape[-1]
     out = _lib.empty((F,))
-    rc = lib.holo_gwb_expectation(_lib.ptr(number), _lib.ptr(hc2), number.numel() // F, F, _lib.ptr(out), _lib.stream())
+    ws = _lib.empty((lib.holo_gwb_expectation_workspace_bytes(F) // 8,))
+    rc = lib.holo_gwb_expectation(_lib.ptr(number), _lib.ptr(hc2), number.numel() // F, F, _lib.ptr(out), _lib.ptr(ws),
+                                  ws.numel() * 8, _lib.stream())
     _lib.check(rc, "gwb_expectation")
     return out
 

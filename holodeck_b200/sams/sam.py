@@ -174,12 +174,22 @@ class Semi_Analytic_Model:
         gsmf, gpf, gmt, gmr, mmb = self._gsmf, self._gpf, self._gmt, self._gmr, self._mmbulge
 
         def fusable(obj, classes, what):
-            ok = (type(obj) in classes) or (
-                isinstance(obj, classes) and type(obj).__call__ in [cc.__call__ for cc in classes])
+            # The kernel evaluates the closed form from `_kernel_params()` alone: a subclass that overrides ANY method
+            # (`__call__`, `_phi_func`, `zprime`, ...) would be silently ignored on the device, so only the exact
+            # classes -- or subclasses that add nothing but new default parameters through `__init__` -- are accepted.
+            ok = type(obj) in classes
+            if not ok and isinstance(obj, classes):
+                base = next(cc for cc in classes if isinstance(obj, cc))
+                added = set()
+                for klass in type(obj).__mro__:
+                    if klass is base:
+                        break
+                    added |= {nn for nn, vv in vars(klass).items() if callable(vv) or isinstance(vv, property)}
+                ok = added <= {"__init__"}
             if not ok:
                 raise NotImplementedError(
                     f"{what} {obj!r}: only the closed-form reference classes {[cc.__name__ for cc in classes]} "
-                    "(or subclasses that do not override `__call__`) can be fused into the CUDA density "
+                    "(or subclasses that override nothing but `__init__`) can be fused into the CUDA density "
                     "kernel; holodeck_b200 has no CPU fallback for user-defined components.")
 
         fusable(gsmf, (GSMF_Schechter, GSMF_Double_Schechter), "gsmf")

@@ -34,7 +34,7 @@ extern "C" {
 #define HOLO_ERR_CUDA 2
 #define HOLO_ERR_OVERFLOW 3 /* loudest-source event buckets overflowed or head too short: retry bigger */
 
-#define HOLO_ABI_VERSION 2
+#define HOLO_ABI_VERSION 3
 
 int holo_abi_version(void);
 const char* holo_last_error(void);
@@ -201,8 +201,9 @@ int holo_integrate_and_strain(const holo_cosmo_params* cosmo_host, double gw_src
                               void* stream);
 
 /* hc2[f] = sum_{m,q,z} number * h2fdf   (realize=False branch, gravwaves.py:481-485, 557-561) */
+int64_t holo_gwb_expectation_workspace_bytes(int F);
 int holo_gwb_expectation(const double* number, const double* h2fdf, int64_t ncell, int F,
-                         double* hc2 /* (F,) */, void* stream);
+                         double* hc2 /* (F,) */, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K3/K4  realised GWB and loudest-source split.

@@ -17,12 +17,13 @@ import numpy as np
 from oracle import glue as G
 
 
-def classic_workload(shape=(91, 81, 101), nfreqs=40, pta_dur_yr=16.03):
-    """BASELINE.json configs[1]: PS_Classic-default SAM (librarian/param_spaces_classic.py:13-42) without
-    M-Mbulge scatter, Fixed_Time_2PL_SAM(3 Gyr, 1e4 pc, 100 pc, -1, +2.5, 300 steps), pta_freqs(16.03 yr, 40)."""
+def classic_workload(shape=(91, 81, 101), nfreqs=40, pta_dur_yr=16.03, scatter_dex=0.0):
+    """BASELINE.json configs[1]: PS_Classic-default SAM (librarian/param_spaces_classic.py:13-42),
+    Fixed_Time_2PL_SAM(3 Gyr, 1e4 pc, 100 pc, -1, +2.5, 300 steps), pta_freqs(16.03 yr, 40).  `scatter_dex` is the
+    M-Mbulge scatter (PS_Classic's own default is 0.3, param_spaces_classic.py:41; 0 skips `add_scatter_to_masses`)."""
     pp = dict(G.PS_CLASSIC_DEFAULTS)
     M, Q, Z = shape
-    wl = dict(params=pp, shape=tuple(shape), nfreqs=nfreqs, pta_dur_yr=pta_dur_yr)
+    wl = dict(params=pp, shape=tuple(shape), nfreqs=nfreqs, pta_dur_yr=pta_dur_yr, scatter_dex=float(scatter_dex))
     wl["mtot"] = np.logspace(*np.log10([1.0e4*G.MSOL, 1.0e12*G.MSOL]), M)
     wl["mrat"] = np.logspace(*np.log10([1e-3, 1.0]), Q)
     wl["redz"] = np.logspace(*np.log10([1e-3, 10.0]), Z)
@@ -35,11 +36,11 @@ def classic_workload(shape=(91, 81, 101), nfreqs=40, pta_dur_yr=16.03):
 def reference_density(wl, cosmo_tables=None):
     pp = wl["params"]
     oc = G.OracleCosmo(closed_form=True)
-    mmb = G.MMBulge('KH2013', mamp_log10=pp['mmb_mamp_log10'], mplaw=pp['mmb_plaw'], scatter_dex=0.0)
+    mmb = G.MMBulge('KH2013', mamp_log10=pp['mmb_mamp_log10'], mplaw=pp['mmb_plaw'], scatter_dex=wl.get("scatter_dex", 0.0))
     gsmf = lambda m, z: G.gsmf_schechter(m, z, phi0=pp['gsmf_phi0_log10'], phiz=pp['gsmf_phiz'], mchar0_log10=pp['gsmf_mchar0_log10'], mcharz=pp['gsmf_mcharz'], alpha0=pp['gsmf_alpha0'], alphaz=pp['gsmf_alphaz'])   # noqa
     gpf = lambda m, q, z: G.gpf_power_law(m, q, z, frac_norm_allq=pp['gpf_frac_norm_allq'], malpha=pp['gpf_malpha'], qgamma=pp['gpf_qgamma'], zbeta=pp['gpf_zbeta'], max_frac=pp['gpf_max_frac'])   # noqa
     gmt = lambda m, q, z: G.gmt_power_law(m, q, z, oc.h, time_norm=pp['gmt_norm']*G.GYR, malpha=pp['gmt_malpha'], qgamma=pp['gmt_qgamma'], zbeta=pp['gmt_zbeta'])   # noqa
-    dd = G.static_binary_density(wl["mtot"], wl["mrat"], wl["redz"], oc, gsmf, mmb, gpf=gpf, gmt=gmt, scatter=False)
+    dd = G.static_binary_density(wl["mtot"], wl["mrat"], wl["redz"], oc, gsmf, mmb, gpf=gpf, gmt=gmt, scatter=wl.get("scatter_dex", 0.0) > 0.0)
     return oc, dd
 
 
@@ -85,7 +86,8 @@ def reference_deterministic(wl):
     _, msort, qsort, zsort = G.rank_order(h2fdf, 'stable')
     tt["strain_sort"] = time.perf_counter() - t0
     state = dict(edges=edges, redz_final=rz, diff_num=dn, number=number, h2fdf=h2fdf,
-                 msort=msort, qsort=qsort, zsort=zsort, norm_log10=norm_log10, dens=dd["dens"])
+                 msort=msort, qsort=qsort, zsort=zsort, norm_log10=norm_log10, dens=dd["dens"],
+                 gmt_time=dd["gmt_time"], redz_prime=dd["redz_prime"], dens_noscatter=dd["dens_noscatter"])
     return state, tt
 
 

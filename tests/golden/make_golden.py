@@ -174,8 +174,37 @@ def eccen_case(name="eccen_small"):
     print(f"{fname.name}: {fname.stat().st_size/1e6:.2f} MB")
 
 
+def eccen_case_h100(name="eccen_h100"):
+    """BASELINE configs[3] harmonic count: `sam_calc_gwb_single_eccen` at H = 100 on a 21^3 grid, 8 frequencies
+    (11 s of the compiled reference per track)."""
+    cy, _, _ = G.ref()
+    M, Q, Z, F, H, E = 21, 21, 21, 8, 100, 123
+    mtot = np.logspace(np.log10(1e6*G.MSOL), np.log10(1e11*G.MSOL), M)
+    mrat = np.logspace(-2, 0, Q)
+    redz = np.logspace(-2, 0.7, Z)
+    rng = np.random.default_rng(11)
+    ndens = rng.uniform(0, 1e-3, (M, Q, Z))
+    ndens[rng.uniform(size=ndens.shape) < 0.2] = 0.0
+    oc = G.OracleCosmo()
+    dcom = oc.comoving_distance(redz) / G.MPC
+    fobs, _ = G.pta_freqs(16.03*G.YR, F)
+    out = dict(ndens=ndens, mtot=mtot, mrat=mrat, redz=redz, dcom=dcom, fobs=fobs, nharms=H)
+    for tag, a0 in (("a", 0.05*G.PC), ("b", 10.0*G.PC)):
+        sepa, ecc = G.evolve_eccen_uniform_single(mtot, 0.95, a0, E)
+        out[f"sepa_{tag}"] = sepa
+        out[f"eccen_{tag}"] = ecc
+        out[f"gwb_{tag}"] = np.asarray(cy.sam_calc_gwb_single_eccen(ndens, np.log10(mtot), mrat, redz, dcom, fobs, sepa, ecc, H))
+    fname = OUT / f"{name}.npz"
+    np.savez_compressed(fname, **out)
+    print(f"{fname.name}: {fname.stat().st_size/1e6:.2f} MB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "eccen_h100":
+        eccen_case_h100()
+        sys.exit(0)
     sam_case("classic_2pwl", (13, 11, 15), 6, 16.03, 'classic', seed=12345, nreals=6, nloud=3)
     sam_case("default_gw", (10, 11, 12), 5, 10.0, 'default', seed=777, nreals=5, nloud=2, hard='gw')
     sam_case("double_2pwl", (9, 8, 10), 4, 16.03, 'double', seed=99, nreals=4, nloud=5)
     eccen_case()
+    eccen_case_h100()

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, name), f"{name} declared in include/holo_b200.h but not exported"
     # every declared function has a ctypes signature, and nothing undeclared is bound
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert lib.holo_abi_version() == 2
+    assert lib.holo_abi_version() == 3
     assert isinstance(lib.holo_last_error(), bytes)
     assert lib.holo_launch_count() >= 0
 

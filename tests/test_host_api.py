@@ -57,6 +57,18 @@ def test_unfusable_components_are_rejected_not_emulated():
     sam = sams.Semi_Analytic_Model(gsmf=MyGSMF, shape=6)
     with pytest.raises(NotImplementedError):
         sam._kernel_params()
+    # overriding a HELPER the host __call__ uses would be ignored by the kernel (it reads `_kernel_params()` only)
+    class HelperGSMF(sams.GSMF_Schechter):
+        def _phi_func(self, redz):
+            return 1.0 + 0.0 * redz
+    with pytest.raises(NotImplementedError):
+        sams.Semi_Analytic_Model(gsmf=HelperGSMF, shape=6)._kernel_params()
+
+    # ... while a subclass that only sets new defaults is the same closed form
+    class MyDefaults(sams.GSMF_Schechter):
+        def __init__(self):
+            super().__init__(phi0=-2.5)
+    assert sams.Semi_Analytic_Model(gsmf=MyDefaults, shape=6)._kernel_params().gsmf[0] == -2.5
     ok = sams.Semi_Analytic_Model(gsmf=sams.GSMF_Double_Schechter, gpf=sams.GPF_Power_Law, shape=6)._kernel_params()
     assert ok.gsmf_kind == 1 and ok.use_gmr == 0 and ok.has_gmt == 1 and ok.mmb[1] == 1.17
 
@@ -181,3 +193,20 @@ def test_comoving_distance_table_against_independent_quadrature():
     oc = glue.OracleCosmo()
     want = np.array([oc.comoving_distance(zz) for zz in zs])
     assert np.max(np.abs(got / want - 1.0)) < 1e-13
+
+
+def test_loudest_retry_schedule_fits_the_resolver():
+    """the bucket of a retry is sized from its head margin and never exceeds what `holo_loudest` accepts
+    (RES_WARPS * 2 * cap * 16 B <= 200 KB -> cap <= 1600)."""
+    from holodeck_b200 import cyutils
+    for L in (1, 5, 10, 100, 400):
+        prev = 0.0
+        for attempt in range(1, cyutils._MAX_RETRY):
+            margin, cap = cyutils._retry_schedule(L, attempt)
+            assert cap <= 1600 and 4 * 2 * cap * 16 <= 200 * 1024
+            assert margin >= prev
+            prev = margin
+            if cap < cyutils._MAX_BUCKET_CAP:
+                assert cap >= 2.0 * (L + margin) + 64.0       # the expected L + margin events fit with slack
+            else:
+                assert L + margin <= cap                      # clamped: the head is cut to what the bucket holds
