@@ -315,24 +315,36 @@ def run_b200(args):
     ncell = (M - 1) * (Q - 1) * (Z - 1) * args.nfreqs
     seed = 12345
 
-    def gather(tt):
-        if world == 1:
-            return tt
-        outs = [torch.empty_like(tt) for _ in range(world)]
-        dist.all_gather(outs, tt)
-        return torch.cat(outs, dim=1)
+    from holodeck_b200 import dist as hdist
+    gbuf = {"buf": None, "pin": None}
+
+    def gather(hc_ss, hc_bg):
+        """ONE all_gather_into_tensor per step for both tables, into a buffer that lives across steps"""
+        (g_ss, g_bg), gbuf["buf"] = hdist.gather_tables([hc_ss, hc_bg], out=gbuf["buf"])
+        return g_ss, g_bg
 
     def step_device():
         sam, hard = make_models(args)
         hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0, device=True)
-        return gather(hc_ss), gather(hc_bg)
+        return gather(hc_ss, hc_bg)
 
     def step_e2e():
         sam, hard = make_models(args)
         if world == 1:
             return sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0)
         hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0, device=True)
-        return _lib.to_host(gather(hc_ss)), _lib.to_host(gather(hc_bg))
+        g_ss, g_bg = gather(hc_ss, hc_bg)
+        if rank != 0:
+            return g_ss, g_bg
+        # the job's result is read on rank 0 only: one copy of the packed gather buffer into pinned memory
+        buf = gbuf["buf"]
+        if gbuf["pin"] is None or gbuf["pin"].shape != buf.shape:
+            gbuf["pin"] = torch.empty(buf.shape, dtype=buf.dtype).pin_memory()
+        gbuf["pin"].copy_(buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        _lib.TRAFFIC["d2h"] += buf.numel() * buf.element_size()
+        full = gbuf["pin"].numpy().transpose(1, 0, 2)                       # (F, N*R, L + 1)
+        return full[:, :, :L], full[:, :, L]
 
     def barrier():
         if world > 1:
@@ -398,7 +410,8 @@ def run_b200(args):
     d2h = _lib.TRAFFIC["d2h"] // args.steps
     e2e_value = world * ncell * R * args.steps / (ms_e2e * 1e-3)
     assert out_e2e[0].shape == (args.nfreqs, R * world, L) and out_e2e[1].shape == (args.nfreqs, R * world)
-    assert np.all(np.isfinite(out_e2e[1])) and np.all(out_e2e[1] > 0)
+    if rank == 0:
+        assert np.all(np.isfinite(out_e2e[1])) and np.all(out_e2e[1] > 0)
 
     # ---- the same step with the PS_Classic M-Mbulge scatter (0.3 dex) switched on: K6 runs once per SAM between
     #      the density kernel and the stalled-bin zeroing (reported beside the headline, which keeps
@@ -406,7 +419,7 @@ def run_b200(args):
     def step_scatter():
         sam, hard = make_models(args, scatter_dex=0.3)
         hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0, device=True)
-        return gather(hc_ss), gather(hc_bg)
+        return gather(hc_ss, hc_bg)
     timed(step_scatter, 4)
     ms_scatter, _, _, _ = timed(step_scatter, args.steps)
 

@@ -87,6 +87,9 @@ def sam_lib_combine(path_output, log=None, path_pspace=None, recreate=False, gwb
 
     if path_pspace is None:
         path_pspace = path_output
+    from holodeck_b200.librarian import stream
+    if stream.LibraryStore.exists(path_output):
+        return _combine_from_store(path_output, path_pspace, lib_path, gwb_only, log)
     pspace, pspace_fname = load_pspace_from_path(path_pspace, log=log)
     log.info(f"loaded param space: {pspace} from '{pspace_fname}'")
     param_names = pspace.param_names
@@ -134,6 +137,12 @@ def sam_lib_combine(path_output, log=None, path_pspace=None, recreate=False, gwb
     attrs = dict(param_names=np.array(param_names).astype('S'), parameter_space_class_name=pspace.name,
                  holodeck_version=holo.__version__, holodeck_git_hash="None",
                  holodeck_librarian_version=holo.librarian.__version__)
+    _write_library(lib_path, datasets, attrs, log)
+    assert np.all(fobs_cents > 0.0)
+    return lib_path
+
+
+def _write_library(lib_path, datasets, attrs, log):
     log.info(f"Writing collected data to file {lib_path}")
     if lib_path.suffix == ".hdf5":
         import h5py
@@ -144,6 +153,41 @@ def sam_lib_combine(path_output, log=None, path_pspace=None, recreate=False, gwb
                 h5.attrs[key] = val
     else:
         np.savez(lib_path, **datasets, **{f"attrs/{key}": np.asarray(val) for key, val in attrs.items()})
+
+
+def _combine_from_store(path_output, path_pspace, lib_path, gwb_only, log):
+    """The library was generated through the streaming file plane (``librarian/stream.py``): the combined arrays
+    already exist as memory maps, rows of failed samples are NaN.  Same datasets / attributes / checks as the
+    per-sample-file path above (``combine.py:86-272``)."""
+    from holodeck_b200.librarian import stream
+    store = stream.LibraryStore.open(path_output, mode="r")
+    pspace, pspace_fname = load_pspace_from_path(path_pspace, log=log)
+    log.info(f"loaded param space: {pspace} from '{pspace_fname}'")
+    param_samples = pspace.param_samples[()]
+    if param_samples is None:
+        raise DomainNotLibraryError(f"`library` is True, but {path_output} looks like it's a domain.")
+    param_samples = np.array(param_samples, dtype=np.float64)
+    status = np.asarray(store.status)
+    todo = np.flatnonzero(status == stream.STATUS_TODO)
+    if todo.size:
+        err = f"Missing at least sample number {int(todo[0])} out of {status.size} samples!  ({todo.size} not run yet)"
+        log.exception(err)
+        raise ValueError(err)
+    bad = status == stream.STATUS_FAIL
+    log.info(f"{int(bad.sum())}/{bad.size} files are failures")
+    param_samples[bad] = np.nan
+    has_gwb = 'gwb' in store.maps
+    if gwb_only and not has_gwb:
+        raise RuntimeError(f"Combining with {gwb_only=}, but the library holds no `gwb`!")
+    fobs_cents, fobs_edges = store.fobs
+    datasets = dict(fobs_cents=fobs_cents, fobs_edges=fobs_edges, sample_params=param_samples)
+    for key in ('gwb', 'hc_ss', 'hc_bg', 'sspar', 'bgpar'):
+        if key in store.maps and (key == 'gwb' or not gwb_only):
+            datasets[key] = store.maps[key]
+    attrs = dict(param_names=np.array(pspace.param_names).astype('S'), parameter_space_class_name=pspace.name,
+                 holodeck_version=holo.__version__, holodeck_git_hash="None",
+                 holodeck_librarian_version=holo.librarian.__version__)
+    _write_library(lib_path, datasets, attrs, log)
     assert np.all(fobs_cents > 0.0)
     return lib_path
 

@@ -297,7 +297,7 @@ class PD_Normal(_Param_Dist):
 def run_model(
     sam, hard,
     pta_dur=DEF_PTA_DUR, nfreqs=DEF_NUM_FBINS, nreals=DEF_NUM_REALS, nloudest=DEF_NUM_LOUDEST,
-    gwb_flag=True, singles_flag=True, details_flag=False, params_flag=False, log=None, *, seed=None,
+    gwb_flag=True, singles_flag=True, details_flag=False, params_flag=False, log=None, *, seed=None, device=False,
 ):
     """Run the given SAM + hardening model to produce GW signals (``lib_tools.py:714-842``).
 
@@ -305,7 +305,9 @@ def run_model(
     ``hc_bg (F,R)``, ``sspar (4,F,R,L)``, ``bgpar (7,F,R)``, ``gwb (F,R)``.  As in the reference the
     single-source split and the GWB use independent Poisson draws of the same number grid.
     ``details_flag`` adds ``static_binary_density, number, redz_final, gwb_params, num_params, gwb_mtot_redz_final,
-    num_mtot_redz_final`` (``_calc_model_details``, K7).
+    num_mtot_redz_final`` (``_calc_model_details``, K7).  Keyword-only additions: ``seed``; ``device=True`` leaves
+    ``hc_ss, hc_bg, sspar, bgpar, gwb`` on the GPU as CUDA tensors (the streaming library writer copies them out
+    asynchronously, ``librarian/stream.py``).
     """
     from holodeck_b200.sams import sam_cyutils
     from holodeck_b200 import gravwaves, single_sources
@@ -355,7 +357,7 @@ def run_model(
         # same pass of the realization kernel produces both, with independent Philox streams and seeds
         vals = single_sources.ss_gws_redz(
             edges, use_redz, number, realize=nreals, loudest=nloudest, params=params_flag,
-            seed=None if sub is None else int(sub[0]), _precomputed=strain,
+            seed=None if sub is None else int(sub[0]), _precomputed=strain, device=bool(device),
             _gwb=(nreals, None if sub is None else int(sub[1])) if gwb_flag else None,
         )
         if gwb_flag:
@@ -375,7 +377,7 @@ def run_model(
             gwb = fused_gwb
         else:
             gwb = gravwaves._gws_from_hc2(strain["h2fdf"], number, nreals, True,
-                                          None if sub is None else int(sub[1]), 0, False)
+                                          None if sub is None else int(sub[1]), 0, bool(device))
         data['gwb'] = gwb
 
     return data

@@ -104,7 +104,7 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
         bad = (sspar[3] < 0) & (sspar[3] != -1)
         if bool(bad.any()):
             err = int(bad.sum())
-            err = f"check 1: {err} out of {sspar[3].size} sspar[3] are negative and not -1 in sings.ss_gws_redz()"
+            err = f"check 1: {err} out of {int(np.prod(sspar[3].shape))} sspar[3] are negative and not -1 in sings.ss_gws_redz()"
             raise ValueError(err)
         return (hc_ss, hc_bg, sspar, bgpar) + extra
 

@@ -33,10 +33,12 @@ def test_run_model_all_registered_param_spaces():
 
 def test_gen_lib_writes_reference_file_layout(tmp_path):
     from holodeck_b200 import librarian
-    from holodeck_b200.librarian import gen_lib
+    from holodeck_b200.librarian import gen_lib, combine, stream
     space = librarian.PS_Classic_Phenom_Uniform(nsamples=4, sam_shape=11, seed=2)
     space.param_samples[:, space.param_names.index("mmb_scatter_dex")] = 0.0
-    done, fails = gen_lib.run_library(space, tmp_path, nreals=5, nfreqs=6, nloudest=2, params_flag=True, seed=2)
+    kw = dict(nreals=5, nfreqs=6, nloudest=2, params_flag=True, seed=2)
+    # streaming file plane (default) + the reference's per-sample files from the writer thread
+    done, fails = gen_lib.run_library(space, tmp_path, sim_files=True, **kw)
     assert (done, fails) == (4, 0)
     files = sorted((tmp_path / "library_sims").glob("library__p*.npz"))
     assert [ff.name for ff in files] == [f"library__p{ii:06d}.npz" for ii in range(4)]
@@ -44,10 +46,30 @@ def test_gen_lib_writes_reference_file_layout(tmp_path):
     for key in ("fobs_cents", "fobs_edges", "gwb", "hc_ss", "hc_bg", "sspar", "bgpar", "params", "param_names"):
         assert key in data.files, key
     assert data["gwb"].shape == (6, 5) and data["hc_ss"].shape == (6, 5, 2)
-    assert (tmp_path / "PS_Classic_Phenom_Uniform.pspace.npz").exists()
-    # a second run skips existing files (gen_lib.py:287-296)
-    done2, _ = gen_lib.run_library(space, tmp_path, nreals=5, nfreqs=6, nloudest=2, params_flag=True, seed=2)
+    assert (tmp_path / "PS_Classic_Phenom_Uniform.pspace.npz").exists() and (tmp_path / "config.json").exists()
+    # the memory-mapped combined layout holds the same rows, and combines into the reference's library file
+    store = stream.LibraryStore.open(tmp_path, mode="r")
+    assert all(store.is_done(ii) for ii in range(4))
+    lib = np.load(combine.sam_lib_combine(tmp_path))
+    assert lib["sspar"].shape == (4, 4, 6, 5, 2) and lib["bgpar"].shape == (4, 7, 6, 5)
+    for ii, ff in enumerate(files):
+        one = np.load(ff)
+        for key in ("gwb", "hc_ss", "hc_bg", "sspar", "bgpar"):
+            assert np.array_equal(lib[key][ii], one[key], equal_nan=True), (ii, key)
+        assert np.array_equal(lib["sample_params"][ii], one["params"])
+    # a second run skips finished samples (gen_lib.py:287-296); other settings in the same directory are refused
+    done2, _ = gen_lib.run_library(space, tmp_path, sim_files=True, **kw)
     assert done2 == 4
+    with pytest.raises(RuntimeError, match="different settings"):
+        gen_lib.run_library(space, tmp_path, **dict(kw, nreals=7))
+    # the reference's own file plane (synchronous per-sample files, merged afterwards) gives the same library
+    other = tmp_path / "per_sample"
+    other.mkdir()
+    done3, _ = gen_lib.run_library(space, other, streaming=False, **kw)
+    assert done3 == 4
+    lib2 = np.load(combine.sam_lib_combine(other))
+    for key in ("gwb", "hc_ss", "hc_bg", "sspar", "bgpar", "sample_params"):
+        assert np.array_equal(lib[key], lib2[key], equal_nan=True), key
 
 
 def test_scatter_path_runs_and_conserves_mass():

@@ -210,3 +210,57 @@ def test_loudest_retry_schedule_fits_the_resolver():
                 assert cap >= 2.0 * (L + margin) + 64.0       # the expected L + margin events fit with slack
             else:
                 assert L + margin <= cap                      # clamped: the head is cut to what the bucket holds
+
+
+def test_streaming_store_and_combine(tmp_path):
+    """N2: rows written through `AsyncSampleWriter` into the memory-mapped combined layout come back from
+    `sam_lib_combine` exactly like rows merged from per-sample files; failures are NaN rows; a store with a different
+    layout is refused (resume must not mix shapes)."""
+    import holodeck_b200 as holo
+    from holodeck_b200.librarian import combine, stream
+    S, F, R, L = 6, 5, 4, 3
+    space = holo.librarian.PS_Classic_Phenom_Uniform(nsamples=S, seed=3)
+    space.save(tmp_path)
+    fc = np.arange(1, F + 1) / 5e8
+    fe = (np.arange(F + 1) + 0.5) / 5e8
+    store = stream.LibraryStore.create(tmp_path, S, F, R, L, True, True, True, fc, fe)
+    assert stream.LibraryStore.exists(tmp_path) and not store.is_done(0)
+    with pytest.raises(RuntimeError):
+        stream.LibraryStore.create(tmp_path, S, F, R + 1, L, True, True, True, fc, fe)
+    rng = np.random.default_rng(1)
+    want = {}
+    writer = stream.AsyncSampleWriter(stream.LibraryStore.open(tmp_path), nslots=2)
+    for pnum in (4, 0, 3, 1, 5):
+        want[pnum] = dict(gwb=rng.uniform(size=(F, R)), hc_ss=rng.uniform(size=(F, R, L)), hc_bg=rng.uniform(size=(F, R)),
+                          sspar=rng.uniform(size=(4, F, R, L)), bgpar=rng.uniform(size=(7, F, R)))
+        writer.submit(pnum, dict(want[pnum], fobs_cents=fc))
+    writer.close()
+    with pytest.raises(ValueError, match="sample number 2"):
+        combine.sam_lib_combine(tmp_path, holo.log)                 # sample 2 has not run
+    writer = stream.AsyncSampleWriter(stream.LibraryStore.open(tmp_path))
+    writer.submit_failure(2, "boom")
+    writer.close()
+    again = stream.LibraryStore.open(tmp_path)
+    assert again.is_done(4) and not again.is_done(2)                # a failure is re-attempted by the next run
+    lib_path = combine.sam_lib_combine(tmp_path, holo.log)
+    assert lib_path.suffix == ".npz"
+    lib = np.load(lib_path)
+    for pnum, dd in want.items():
+        for kk, vv in dd.items():
+            assert np.array_equal(lib[kk][pnum], vv), (pnum, kk)
+        assert np.array_equal(lib["sample_params"][pnum], space.param_samples[pnum])
+    assert np.all(np.isnan(lib["gwb"][2])) and np.all(np.isnan(lib["sspar"][2])) and np.all(np.isnan(lib["sample_params"][2]))
+    assert np.array_equal(lib["fobs_edges"], fe)
+    assert "boom" in (tmp_path / stream.DIRNAME_LIBRARY_STORE / "failures.log").read_text()
+
+
+def test_gen_lib_config_is_saved_and_checked_on_resume(tmp_path):
+    from holodeck_b200.librarian import gen_lib
+    cfg = dict(param_space="PS_Classic_Phenom_Uniform", nsamples=4, nreals=3, nfreqs=5, nloudest=2, pta_dur=16.03,
+               sam_shape=None, gwb_flag=True, ss_flag=True, params_flag=False, seed=9)
+    fname = gen_lib._check_config(tmp_path, cfg)
+    assert fname.name == "config.json" and fname.exists()
+    gen_lib._check_config(tmp_path, dict(cfg))                      # same settings: a resume
+    with pytest.raises(RuntimeError, match="nreals"):
+        gen_lib._check_config(tmp_path, dict(cfg, nreals=7))
+    gen_lib._check_config(tmp_path, dict(cfg, nreals=7), resume_ok=False)     # --recreate starts over
