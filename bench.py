@@ -5,16 +5,17 @@ Contract (see the task statement):  ``python bench.py --gpus N --steps K --warmu
 prints ONE JSON line on rank 0.  For N>1 it is launched under torchrun (one rank per GPU).
 
 Step (this arm)   one full pass of the hot path for BASELINE.json configs[1]: a fresh
-                  ``Semi_Analytic_Model`` (PS_Classic defaults, M-Mbulge scatter off -- the scatter is
-                  the host-scipy "next" row N1 and is not part of the path) -> ``Fixed_Time_2PL_SAM``
-                  (K1a) -> ``sam.gwb(fobs_edges, hard, realize=R, loudest=L)`` (K0, K1b, K2+K2b, rank sort,
-                  K4).  `value` keeps every array on the device; `e2e` is the same call through the public
+                  ``Semi_Analytic_Model`` (PS_Classic defaults INCLUDING its 0.3 dex M-Mbulge scatter,
+                  param_spaces_classic.py:41: density K0 -> scatter K6 -> stalled-bin zeroing) ->
+                  ``Fixed_Time_2PL_SAM`` (K1a) -> ``sam.gwb(fobs_edges, hard, realize=R, loudest=L)`` (K1b, K2+K2b, rank
+                  sort, K4).  `value` keeps every array on the device; `e2e` is the same call through the public
                   numpy API (host edge arrays in, hc_ss / hc_bg numpy out, PCIe copies inside the timing).
-N > 1             realizations shard: every rank runs R realizations (global realization index
-                  r0 = rank*R, so the union is one R*N-realization run), then the per-rank hc arrays are
-                  all-gathered over NCCL.  Weak scaling; value = N*cells*R / max-over-ranks time.
---impl reference  the reference's own CPU path (compiled reference Cython from oracle/_ref driven by
-                  oracle/chain.py), all host cores, on a bounded sample of the same workload.
+N > 1             realizations shard.  ``--scaling weak`` (default): every rank runs R realizations (global index
+                  r0 = rank*R: the union is one R*N-realization run); ``--scaling strong``: the R realizations of the
+                  named metric are split over the ranks.  The per-rank hc tables are gathered with ONE
+                  all_gather_into_tensor (NCCL).  value = cells * (realizations of all ranks) / max-over-ranks time.
+--impl reference  the reference's own CPU path (compiled reference Cython from oracle/_ref + the numpy/scipy glue of
+                  oracle/, driven by oracle/chain.py), all host cores, on a bounded sample of the same workload.
 """
 import argparse
 import gc
@@ -47,9 +48,23 @@ def parse_args():
     ap.add_argument("--realize", type=int, default=1000)
     ap.add_argument("--loudest", type=int, default=1, help="sam.gwb default")
     ap.add_argument("--settle-steps", type=int, default=60, help="untimed steps after the W warm-up steps (clock/allocator settle)")
+    ap.add_argument("--scatter-dex", type=float, default=0.3,
+                    help="M-Mbulge scatter of the SAM: 0.3 is PS_Classic's own default (param_spaces_classic.py:41); 0 = off")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: R realizations PER RANK (default); strong: the R realizations are split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-reals", type=int, default=2, help="realizations in the bounded CPU sample")
     return ap.parse_args()
+
+
+def kernel_source_hash():
+    """short hash of the draw kernel's sources: `profiles/ncu_metrics.json` records the hash it was captured at, so a
+    capture of an older kernel version is flagged instead of being re-printed as if live"""
+    import hashlib
+    hh = hashlib.sha1()
+    for name in ("holo_realize.cu", "holo_rng.cuh"):
+        hh.update((ROOT / "holodeck_b200" / "csrc" / name).read_bytes())
+    return hh.hexdigest()[:12]
 
 
 def peaks():
@@ -175,12 +190,19 @@ def _cpu_worker(args):
     return dt
 
 
-def cpu_reference(args, nproc, nreals_each, state=None, tdet=None):
-    """Bounded sample of the reference CPU path.  Returns (cell_real_per_s, info dict, state, tdet)."""
+def cpu_reference(args, nproc, nreals_each, state=None, tdet=None, scatter_sample=None):
+    """Bounded sample of the reference CPU path.  Returns (cell_real_per_s, info dict, state, tdet).
+
+    The M-Mbulge scatter (`add_scatter_to_masses`, scipy, once per SAM) is part of the workload when
+    `--scatter-dex` > 0: the all-cores arm runs all 101 redshift slices once, spread over the processes (they are
+    independent), and charges every one of the `nproc` side-by-side jobs the full core-seconds; the one-core
+    `cpu_baseline` of the GPU arm times a bounded sample of slices (`scatter_sample`) and extrapolates linearly."""
     from oracle import chain
-    wl = chain.classic_workload(shape=tuple(args.shape), nfreqs=args.nfreqs)
+    wl = chain.classic_workload(shape=tuple(args.shape), nfreqs=args.nfreqs, scatter_dex=args.scatter_dex)
     if state is None:
-        state, tdet = chain.reference_deterministic(wl)
+        state, tdet = chain.reference_deterministic(wl, nproc=nproc, scatter_sample=scatter_sample)
+        if nproc > 1 and "scatter" in tdet and scatter_sample is None:
+            tdet["scatter"] = tdet["scatter"] * nproc          # wall on nproc processes -> core-seconds of one job
     global _STATE
     _STATE = state
     ncell = int(np.prod(state["number"].shape))
@@ -204,6 +226,8 @@ def cpu_reference(args, nproc, nreals_each, state=None, tdet=None):
     t_job = t_det + args.realize * t_real
     value = nproc * ncell * args.realize / t_job
     info = dict(t_deterministic_s=round(t_det, 3), t_per_realization_s=round(t_real, 4), stage_s={kk: round(vv, 3) for kk, vv in tdet.items()})
+    if state.get("scatter_info") is not None:
+        info["scatter_sample"] = state["scatter_info"]
     return value, info, state, tdet
 
 
@@ -224,7 +248,8 @@ def run_reference(args):
     ncell = int(np.prod(state["number"].shape))
     sample = (f"{nproc} processes x 1 realization of loudest_hc_from_sorted (L={args.loudest}) on the full "
               f"{'x'.join(map(str, state['number'].shape))} grid per step, extrapolated linearly to R={args.realize}; "
-              f"deterministic stages (density, 2PL norm, dbn, integrate, strain+argsort) timed once: {info['t_deterministic_s']} s")
+              f"deterministic stages (density, M-Mbulge scatter {args.scatter_dex} dex over all slices, 2PL norm, dbn, integrate, "
+              f"strain+argsort) timed once: {info['t_deterministic_s']} core-s per job")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * ncell * args.realize / value, "higher_is_better": True,   # ms: one step on all host cores
@@ -239,10 +264,12 @@ def run_reference(args):
 
 def workload_config(args):
     M, Q, Z = args.shape
-    return {"workload": f"sam.gwb PS_Classic (scatter off) + Fixed_Time_2PL_SAM(3 Gyr), grid {M}x{Q}x{Z}x{args.nfreqs}, "
+    sc = f"M-Mbulge scatter {args.scatter_dex} dex" if args.scatter_dex > 0 else "scatter off"
+    return {"workload": f"sam.gwb PS_Classic ({sc}) + Fixed_Time_2PL_SAM(3 Gyr), grid {M}x{Q}x{Z}x{args.nfreqs}, "
                         f"realize={args.realize}, loudest={args.loudest}",
             "grid": [M, Q, Z, args.nfreqs], "realize": args.realize, "loudest": args.loudest,
-            "parallelism": f"realization-sharded x{args.gpus}",
+            "mmb_scatter_dex": args.scatter_dex,
+            "parallelism": f"realization-sharded x{args.gpus} ({getattr(args, 'scaling', 'weak')} scaling)",
             "cache": "inputs larger than L2 (2 x 238 MB grids re-streamed every step; no explicit flush)"}
 
 
@@ -250,8 +277,11 @@ def workload_config(args):
 # B200 arm
 # ==================================================================================================
 
-def make_models(args, scatter_dex=0.0):
-    """Fresh SAM + hardening for configs[1] (librarian/param_spaces_classic.py:13-89; M-Mbulge scatter off unless asked)."""
+def make_models(args, scatter_dex=None):
+    """Fresh SAM + hardening for configs[1] (librarian/param_spaces_classic.py:13-89); the M-Mbulge scatter is
+    `args.scatter_dex` (PS_Classic's 0.3 dex by default) unless given."""
+    if scatter_dex is None:
+        scatter_dex = float(getattr(args, "scatter_dex", 0.0))
     import holodeck_b200 as holo
     from holodeck_b200 import sams, host_relations
     from holodeck_b200.constants import GYR, PC
@@ -287,8 +317,13 @@ def deterministic_parity(sam, hard, fobs_edges, state):
     rep["redz_final"] = cmp(rz, state["redz_final"])
     rep["redz_final"]["sentinel_mismatch"] = int(np.count_nonzero((rz == -1.0) != (state["redz_final"] == -1.0)))
     del rz
-    rep["number"] = cmp(_lib.to_host(strain["number"]), state["number"])
-    rep["h2fdf"] = cmp(_lib.to_host(strain["h2fdf"]), state["h2fdf"])
+    number, h2fdf = _lib.to_host(strain["number"]), _lib.to_host(strain["h2fdf"])
+    rep["number"] = cmp(number, state["number"])
+    rep["h2fdf"] = cmp(h2fdf, state["h2fdf"])
+    # the expectation-value spectrum sum(number * h2fdf) per frequency: what the realised spectra scatter about
+    got = np.sum(number * h2fdf, axis=(0, 1, 2))
+    want = np.sum(state["number"] * state["h2fdf"], axis=(0, 1, 2))
+    rep["hc2_expect_max_rel"] = float(np.max(np.abs(got - want) / want))
     return rep
 
 
@@ -309,17 +344,27 @@ def run_b200(args):
     lib = _lib.require_gpu()
 
     fobs_cents, fobs_edges = utils.pta_freqs(16.03*YR, args.nfreqs)
-    R, L = args.realize, args.loudest
-    r0 = rank * R
+    L = args.loudest
+    from holodeck_b200 import dist as hdist
+    if args.scaling == "strong":        # the named R realizations are split over the ranks
+        r0, R = hdist.realization_slice(args.realize, rank, world)
+        Rtot = args.realize
+        even = (args.realize % world == 0)
+    else:                               # every rank draws R realizations of its own: one R*N-realization run
+        R = args.realize
+        r0 = rank * R
+        Rtot = R * world
+        even = True
     M, Q, Z = args.shape
     ncell = (M - 1) * (Q - 1) * (Z - 1) * args.nfreqs
     seed = 12345
 
-    from holodeck_b200 import dist as hdist
     gbuf = {"buf": None, "pin": None}
 
     def gather(hc_ss, hc_bg):
         """ONE all_gather_into_tensor per step for both tables, into a buffer that lives across steps"""
+        if not even:    # ragged strong-scaling split: per-table gather with padding
+            return (hdist.gather_realizations(hc_ss, axis=1, nreals=Rtot), hdist.gather_realizations(hc_bg, axis=1, nreals=Rtot))
         (g_ss, g_bg), gbuf["buf"] = hdist.gather_tables([hc_ss, hc_bg], out=gbuf["buf"])
         return g_ss, g_bg
 
@@ -334,6 +379,8 @@ def run_b200(args):
             return sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0)
         hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0, device=True)
         g_ss, g_bg = gather(hc_ss, hc_bg)
+        if not even:
+            return (_lib.to_host(g_ss), _lib.to_host(g_bg)) if rank == 0 else (g_ss, g_bg)
         if rank != 0:
             return g_ss, g_bg
         # the job's result is read on rank 0 only: one copy of the packed gather buffer into pinned memory
@@ -399,7 +446,7 @@ def run_b200(args):
         print("step_ms", [round(xx, 2) for xx in timed.last_steps], file=sys.stderr)
     steps_ms = sorted(timed.last_steps)
     n_launch = lib.holo_launch_count() - n_launch0
-    value = world * ncell * R * args.steps / (ms_total * 1e-3)
+    value = ncell * Rtot * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the public numpy API
     timed(step_e2e, max(2, min(args.warmup, 4)))
@@ -408,20 +455,34 @@ def run_b200(args):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     h2d = _lib.TRAFFIC["h2d"] // args.steps
     d2h = _lib.TRAFFIC["d2h"] // args.steps
-    e2e_value = world * ncell * R * args.steps / (ms_e2e * 1e-3)
-    assert out_e2e[0].shape == (args.nfreqs, R * world, L) and out_e2e[1].shape == (args.nfreqs, R * world)
+    e2e_value = ncell * Rtot * args.steps / (ms_e2e * 1e-3)
+    assert out_e2e[0].shape == (args.nfreqs, Rtot, L) and out_e2e[1].shape == (args.nfreqs, Rtot)
     if rank == 0:
         assert np.all(np.isfinite(out_e2e[1])) and np.all(out_e2e[1] > 0)
 
-    # ---- the same step with the PS_Classic M-Mbulge scatter (0.3 dex) switched on: K6 runs once per SAM between
-    #      the density kernel and the stalled-bin zeroing (reported beside the headline, which keeps
-    #      the scatter off in both arms so that rounds stay comparable)
-    def step_scatter():
-        sam, hard = make_models(args, scatter_dex=0.3)
+    # ---- the same step WITHOUT the M-Mbulge scatter (round 1's headline configuration; K6 skipped), and with
+    #      loudest = 10 (BASELINE configs[2]: the single-source split), both beside the headline
+    def step_noscatter():
+        sam, hard = make_models(args, scatter_dex=0.0)
         hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=L, seed=seed, r0=r0, device=True)
         return gather(hc_ss, hc_bg)
-    timed(step_scatter, 4)
-    ms_scatter, _, _, _ = timed(step_scatter, args.steps)
+    timed(step_noscatter, 4)
+    ms_noscatter, _, _, _ = timed(step_noscatter, args.steps)
+    gbuf["buf"] = None
+
+    def step_loud10():
+        sam, hard = make_models(args)
+        hc_ss, hc_bg = sam.gwb(fobs_edges, hard, realize=R, loudest=10, seed=seed, r0=r0, device=True)
+        return gather(hc_ss, hc_bg)
+    timed(step_loud10, 4)
+    ms_loud10, _, _, _ = timed(step_loud10, args.steps)
+    gbuf["buf"] = None
+
+    def step_loud10_params():
+        sam, hard = make_models(args)
+        return sam.gwb(fobs_edges, hard, realize=R, loudest=10, params=True, seed=seed, r0=r0, device=True)
+    timed(step_loud10_params, 3)
+    ms_loud10p, _, _, _ = timed(step_loud10_params, args.steps)
 
     # ---- one librarian sample (BASELINE configs[4] inner call, lib_tools.run_model: R=100, 5 loudest, parameters
     #      and an independently drawn GWB -- both from one fused pass of the realization kernel), through the numpy API
@@ -457,12 +518,29 @@ def run_b200(args):
         ncu = json.loads((ROOT / "profiles" / "ncu_metrics.json").read_text())
     except Exception:
         pass
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": ncu.get(dom, {}).get("dram_bytes_per_launch"),
-                "peak_source": pk["source"], "ms": stages[dom], "algorithmic_bytes": alg_bytes[dom],
-                "note": ("the dominant kernel draws R Poisson counts per grid element out of shared memory: it is bound by "
-                         "instruction issue, not HBM (see kernels.loudest_draw); `traffic` is per launch from "
-                         "profiles/ncu_metrics.json")}
+    hbm_view = {"achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "algorithmic_bytes": alg_bytes[dom]}
+    clk_mhz = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
+    cap = ncu.get(dom, {})
+    stale = cap.get("source_hash") not in (None, kernel_source_hash())
+    if dom == "loudest_draw" and cap.get("warp_inst_per_launch"):
+        # The dominant kernel draws R Poisson counts per grid element out of shared memory (0.016 B of HBM per
+        # cell-realization): it is bound by INSTRUCTION ISSUE.  achieved = warp instructions of one launch (ncu
+        # `smsp__inst_executed.sum` of the same kernel, profiles/) / its live CUDA-event duration in this run;
+        # peak = 148 SMs x 4 schedulers x 1 warp instruction per clock at the SM clock sampled during the run.
+        wi = float(cap["warp_inst_per_launch"])
+        ach_i = wi / (stages[dom] * 1e-3) / 1e9
+        peak_i = 148 * 4 * clk_mhz * 1e6 / 1e9
+        roofline = {"kernel": dom, "bound": "issue", "achieved": ach_i, "peak": peak_i, "unit": "Gwarp-inst/s",
+                    "frac": ach_i / peak_i, "traffic": cap.get("dram_bytes_per_launch"), "ms": stages[dom],
+                    "warp_inst_per_launch": wi, "inst_source": cap.get("source"), "inst_capture_stale": bool(stale),
+                    "peak_source": f"148 SM x 4 issue slots x {clk_mhz:.0f} MHz (sampled)", "hbm": hbm_view,
+                    "note": ("issue-bound kernel: `frac` is issue-slot use (ncu sm issue-active agrees: "
+                             f"{cap.get('issue_active_pct')} %); `hbm` is the same launch against the measured HBM peak; "
+                             "`traffic` = dram read+write bytes per launch from the same ncu capture")}
+    else:
+        roofline = {"kernel": dom, "bound": "hbm", **hbm_view, "traffic": cap.get("dram_bytes_per_launch"),
+                    "peak_source": pk["source"], "ms": stages[dom]}
     per_kernel = {}
     for kk, bb in alg_bytes.items():
         if kk in stages and stages[kk] > 0:
@@ -488,7 +566,7 @@ def run_b200(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args),
         "clocks": clocks,
         "step_ms_spread": {"min": round(steps_ms[0], 3), "median": round(steps_ms[len(steps_ms) // 2], 3),
@@ -499,8 +577,12 @@ def run_b200(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(n_launch),
         "loudest_retries": int(__import__("holodeck_b200").cyutils.STATS["loudest_retries"]),
-        "mmbulge_scatter_on": {"ms_per_step": ms_scatter / args.steps, "value": world * ncell * R * args.steps / (ms_scatter * 1e-3),
-                               "note": "same step with mmb_scatter_dex=0.3 (K6 on the device, once per SAM)"},
+        "mmbulge_scatter_off": {"ms_per_step": ms_noscatter / args.steps, "value": ncell * Rtot * args.steps / (ms_noscatter * 1e-3),
+                                "note": "same step with mmb_scatter_dex=0 (round 1's headline configuration: K6 skipped)"},
+        "config3_loudest10": {"ms_per_step": ms_loud10 / args.steps, "value": ncell * Rtot * args.steps / (ms_loud10 * 1e-3),
+                              "note": "BASELINE configs[2]: same step with loudest=10 (ss_gws_redz nloudest=10)"},
+        "config3_loudest10_params": {"ms_per_step": ms_loud10p / args.steps, "value": ncell * Rtot * args.steps / (ms_loud10p * 1e-3),
+                                     "note": "same with params=True (sspar, bgpar): the variant run_model uses; no gather"},
         "library_sample": {"ms_per_sample": ms_lib / args.steps, "samples_per_s": world * args.steps / (ms_lib * 1e-3),
                            "note": "librarian.run_model on the same grid: nreals=100, nloudest=5, params + gwb (one sample "
                                    "per rank at a time; BASELINE configs[4] shards 2000 such samples over the ranks)"},
@@ -510,12 +592,26 @@ def run_b200(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
-            val, info, _, _ = cpu_reference(args, 1, args.cpu_reals)
+            val, info, _, _ = cpu_reference(args, 1, args.cpu_reals, scatter_sample=11 if args.scatter_dex > 0 else None)
             line["cpu_baseline"] = {
                 "value": val, "unit": UNIT, "cores": 1, "kind": "reference",
-                "sample": (f"reference chain on the same workload: deterministic stages once + {args.cpu_reals} realizations of "
-                           f"loudest_hc_from_sorted (compiled reference, oracle/_ref), extrapolated linearly to R={R}"),
+                "sample": (f"reference chain on the same workload on ONE core: deterministic stages once (M-Mbulge scatter: 11 of "
+                           f"{Z} redshift slices timed, linear in the slice count; the later stages run on the unscattered grid) + "
+                           f"{args.cpu_reals} realizations of loudest_hc_from_sorted (compiled reference, oracle/_ref), "
+                           f"extrapolated linearly to R={R}"),
                 **info}
+            # parity of the very arrays the timed step produces (scatter on) against the oracle chain; the oracle's
+            # scatter (scipy, 101 slices) is spread over the host cores here -- it is the checker, not the baseline
+            from oracle import chain
+            wl = chain.classic_workload(shape=tuple(args.shape), nfreqs=args.nfreqs, scatter_dex=args.scatter_dex)
+            st_full, _ = chain.reference_deterministic(wl, nproc=min(os.cpu_count() or 1, 16))
+            sam, hard = make_models(args)
+            par = deterministic_parity(sam, hard, fobs_edges, st_full)
+            line["parity"] = {"against": "oracle/chain.reference_deterministic on the timed workload (compiled reference + numpy glue)",
+                              **par}
+            worst = max(par[kk]["max_rel"] for kk in ("dens", "number", "h2fdf"))
+            assert par["number"]["zero_mismatch"] == 0 and par["redz_final"]["sentinel_mismatch"] == 0 and worst < 1e-6 \
+                and par["hc2_expect_max_rel"] < 1e-9, f"deterministic parity lost: {par}"
         except Exception as err:   # the oracle did not travel: say so instead of inventing a number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {err}"}
     emit(line)
@@ -543,8 +639,17 @@ def stage_times(args, fobs_edges, R, L, seed, r0):
         marks = [("start", ev())]
         sam, hard = make_models(args)     # K1a runs in the hardening constructor; density is lazy
         marks.append(("norm_2pwl", ev()))
-        sam._static_binary_density_device()
-        marks.append(("density", ev()))
+        if getattr(args, "scatter_dex", 0.0) > 0.0:
+            # K0 alone on a scatter-free twin, then K0 + K6 (+ stalled-bin zeroing) on the timed model
+            twin, _ = make_models(args, scatter_dex=0.0)
+            marks.append(("norm_2pwl_twin", ev()))
+            twin._static_binary_density_device()
+            marks.append(("density", ev()))
+            sam._static_binary_density_device()
+            marks.append(("density_and_scatter", ev()))
+        else:
+            sam._static_binary_density_device()
+            marks.append(("density", ev()))
         fobs_gw_cents = utils.midpoints(fobs_edges)
         redz_final, diff_num = sam_cyutils.dynamic_binary_number_at_fobs(fobs_gw_cents / 2.0, sam, hard, cosmo, device=True)
         marks.append(("dbn_2pwl", ev()))
@@ -560,6 +665,9 @@ def stage_times(args, fobs_edges, R, L, seed, r0):
         prof = (C.c_double * 8)()
         nn = lib.holo_get_profile(prof, 8)
         cur = {marks[ii][0]: marks[ii - 1][1].elapsed_time(marks[ii][1]) for ii in range(1, len(marks))}
+        cur.pop("norm_2pwl_twin", None)
+        if "density_and_scatter" in cur:
+            cur["mmbulge_scatter"] = cur["density_and_scatter"] - cur["density"]
         if nn >= 4:
             cur.update({"loudest_head_prep": prof[0], "loudest_draw": prof[1], "loudest_resolve": prof[2], "loudest_final": prof[3]})
             cur["rank_sort_and_glue"] = cur["ss_gws_redz_total"] - sum(prof[ii] for ii in range(4))

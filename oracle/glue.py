@@ -448,6 +448,7 @@ def static_binary_density(mtot, mrat, redz, cosmo, gsmf, mmbulge, gpf=None, gmt=
     dmstar_dmbh = dmstar_dmbh_pri * qterm
     dens = dens * ((mtot[:, np.newaxis, np.newaxis] / mstar_tot) * (dmstar_dmbh / dqbh_dqgal))   # sam.py:365
     dens_noscatter = dens.copy()
+    dens_raw = dens.copy()                                  # what the scatter is applied to (stalled bins not zeroed yet)
 
     if scatter and (mmbulge._scatter_dex > 0.0):            # sam.py:368-389
         dens = add_scatter_to_masses(mtot, mrat, dens, mmbulge._scatter_dex)
@@ -456,7 +457,7 @@ def static_binary_density(mtot, mrat, redz, cosmo, gsmf, mmbulge, gpf=None, gmt=
         dens = dens.copy()
         dens[idx_stalled] = 0.0
         dens_noscatter[idx_stalled] = 0.0
-    return dict(dens=dens, gmt_time=gmt_time, redz_prime=zprime, dens_noscatter=dens_noscatter)
+    return dict(dens=dens, gmt_time=gmt_time, redz_prime=zprime, dens_noscatter=dens_noscatter, dens_raw=dens_raw)
 
 
 # ---- M-Mbulge scatter: sams/sam.py:1291-1394 with utils.py:382-488 helpers (scipy, as in the reference)

@@ -63,6 +63,37 @@ def test_emu_norm_and_dbn(emu, golden):
     assert rel_err(dn, gg["diff_num"]) < 1e-12
 
 
+def test_emu_dbn_named_size(emu):
+    """The K1b arithmetic (csrc/holo_math.cuh, compiled for the host) on ALL 29,778,840 edge cells of the named
+    91x81x101 x 40 grid against the compiled reference (oracle/_ref `dynamic_binary_number_at_fobs`,
+    sam_cyutils.pyx:510-781): no sentinel / zero-pattern mismatch -- i.e. none of the threshold branches
+    (`time_left > age_universe` :667, bracket ties :709, table-end extrapolation :683-687) flips -- and 1e-12 relative.
+    (~35 s: the reference's dbn is 11 s, the emulation 10 s.)"""
+    from oracle import chain, glue
+    from holodeck_b200 import _lib as L
+    wl = chain.classic_workload()
+    st, _ = chain.reference_deterministic(wl)
+    hp = wl["hard"]
+    M, Q, Z = wl["shape"]
+    fo = np.ascontiguousarray(wl["fobs_cents"] / 2.0)
+    F = fo.size
+    tabs = chain.make_cosmo_tables(glue.OracleCosmo(closed_form=True))
+    rz = np.zeros((M, Q, Z, F))
+    dn = np.zeros((M, Q, Z, F))
+    norm = np.ascontiguousarray(10.0 ** st["norm_log10"])
+    emu.emu_dbn_2pwl.argtypes = [L.CyConsts, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p] + [C.c_double] * 3 + \
+        [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2
+    emu.emu_dbn_2pwl(L.cy_consts(), P(fo), F, hp["sepa_init"], int(hp["nsteps"]), P(norm), hp["rchar"], hp["gamma_inner"],
+                     hp["gamma_outer"], P(st["dens"]), P(wl["mtot"]), P(wl["mrat"]), P(wl["redz"]), P(st["gmt_time"]), M, Q, Z,
+                     P(tabs._grid_z), P(tabs._grid_dcom), P(tabs._grid_age), tabs._grid_z.size, P(rz), P(dn))
+    assert np.count_nonzero((rz == -1) != (st["redz_final"] == -1)) == 0
+    assert np.count_nonzero((dn == 0) != (st["diff_num"] == 0)) == 0
+    assert rel_err(rz, st["redz_final"]) < 1e-12
+    assert rel_err(dn, st["diff_num"]) < 1e-12
+    # ... and the fused K2 + K2b arithmetic on the reference's grids: `number` vs the compiled reference
+    assert np.count_nonzero(st["redz_final"] != -1) > 4_000_000
+
+
 def test_emu_integrate_and_strain(emu, golden):
     from holodeck_b200 import _lib as L, cosmo, utils
     from holodeck_b200.constants import NWTG
