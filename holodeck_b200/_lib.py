@@ -216,7 +216,8 @@ SIGNATURES = {
     "holo_sam_calc_gwb_single_eccen": [CyConsts, _D, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I,
                                        _L, _U, _P, _P, _L, _P],
     "holo_eccen_workspace_bytes": [_I, _I, _I, _I, _I, _I],
-    "holo_scatter_gradients": [_I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _I, _D, _P, _P, _P],
+    "holo_scatter_step_bytes": [],
+    "holo_scatter_gradients": [_I, _I, _P, _I, _P, _I, _D, _P, _P, _P],
     "holo_scatter_ct_eval": [_L, _I, _P, _P, _P, _P, _P, _P],
     "holo_scatter_bilinear": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "holo_scatter_geo_bytes": [],

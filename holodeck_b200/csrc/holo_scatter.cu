@@ -27,7 +27,9 @@
 namespace holo {
 
 constexpr int GS_LANES = 8;                       // lanes cooperating on one vertex (mean degree ~6)
-constexpr int GS_THREADS = 256;                   // 32 vertices of a level at a time
+constexpr int GS_THREADS = 256;
+constexpr int GS_SLOTS = GS_THREADS / GS_LANES;   // vertices of a level processed per step
+constexpr int GS_MAX_STAGE = 4;                   // depth of the step ring in shared memory
 
 // -------------------------------------------------------------------------------------------------
 // K6a: gradients at the triangulation vertices by scipy's Gauss-Seidel sweeps (interpnd.pyx,
@@ -37,63 +39,118 @@ constexpr int GS_THREADS = 256;                   // 32 vertices of a level at a
 // not connected do not interact within a sweep, so the sweep is executed level by level of the dependency
 // graph (level(v) = 1 + max level of its lower-numbered neighbours): every vertex still sees exactly the
 // values the sequential sweep would show it -- same iterates up to rounding, same iteration count -- but a
-// level's vertices run in parallel, and the neighbours of a vertex are summed by GS_LANES cooperating lanes
-// (the per-edge quotients ex/L^3, ey/L^3 and the inverse 2x2 matrices are geometry: precomputed).
+// level's vertices run in parallel, and the neighbours of a vertex are summed by GS_LANES cooperating lanes.
+//
+// The sweep is a chain of ~450 dependent steps (441 levels at the named grid), 1..9 sweeps per slice: what a step
+// costs is latency, and in round 1 that latency was four dependent L2 round trips per step (order -> indptr ->
+// indices -> edge), 5.3 ms per launch.  All of that is geometry.  The host now flattens it into a STEP PROGRAM:
+// one fixed-size record per step holding, per thread, its neighbour index and edge quotients and, per vertex slot,
+// the vertex index and its inverse normal matrix.  A record is one contiguous 10 KB block, so the kernel streams the
+// program through a ring of shared-memory stages with TMA bulk copies (`cp.async.bulk` completing on an mbarrier),
+// issued GS_MAX_STAGE-1 steps ahead by one thread: a step then touches shared memory only.
 // -------------------------------------------------------------------------------------------------
+struct GsRec {                       // one step: <= GS_SLOTS vertices of one level, <= GS_LANES neighbours each
+    double e[GS_THREADS][4];         // per thread: ex, ey, ex/L^3, ey/L^3 of its edge
+    double qinv[GS_SLOTS][4];        // per vertex slot: inverse of the 2x2 normal matrix, row-major
+    int nb[GS_THREADS];              // per thread: neighbour vertex, -1 = none
+    int vip[GS_SLOTS];               // per vertex slot: vertex, -1 = none
+    int hdr[4];                      // [0] bit 0: first round of its vertices (clear the sums), bit 1: last round (update)
+};
+static_assert(sizeof(GsRec) % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "HOLO_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra HOLO_MBAR_DONE;\n\t"
+        "bra HOLO_MBAR_WAIT;\n\t"
+        "HOLO_MBAR_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(GS_THREADS)
-ct_gradients_kernel(int npts, int Z, const int* __restrict__ indptr, const int* __restrict__ indices,
-                    const double* __restrict__ edge /* (nnz, 4): ex, ey, ex/L^3, ey/L^3 */,
-                    const double* __restrict__ qinv /* (npts, 4): inverse of the 2x2 normal matrix, row-major */,
-                    const int* __restrict__ order, const int* __restrict__ level_ptr, int nlevels,
+ct_gradients_kernel(int npts, int Z, const GsRec* __restrict__ prog, int nsteps, int nstage,
                     const double* __restrict__ data /* (npts, Z) */, int maxiter, double tol,
                     double* __restrict__ grad /* (npts, 2, Z) */, int* __restrict__ niter) {
-    extern __shared__ double s_dyn[];
-    double* s_f = s_dyn;                 // (npts)     data of this slice
-    double* s_y = s_dyn + npts;          // (npts, 2)  current gradients
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    GsRec* ring = reinterpret_cast<GsRec*>(s_raw);                                   // (nstage)
+    double* s_f = reinterpret_cast<double*>(s_raw + (size_t)nstage * sizeof(GsRec)); // (npts)     data of this slice
+    double* s_y = s_f + npts;                                                        // (npts, 2)  current gradients
+    __shared__ uint64_t s_full[GS_MAX_STAGE];
     __shared__ double s_err[GS_THREADS / 32];
     __shared__ int s_done;
     const int z = blockIdx.x, tid = threadIdx.x;
     const int sub = tid % GS_LANES, slot = tid / GS_LANES;
+    if (tid == 0) {
+        for (int i = 0; i < nstage; ++i) mbar_init(&s_full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_done = 0;
+    }
     for (int i = tid; i < npts; i += GS_THREADS) {
         s_f[i] = data[(int64_t)i * Z + z];
         s_y[2 * i] = 0.0;
         s_y[2 * i + 1] = 0.0;
     }
-    if (tid == 0) s_done = 0;
     __syncthreads();
+    const long long total = (long long)maxiter * nsteps;       // global step counter g runs over sweeps
+    auto issue = [&](long long g) {                            // (thread 0) stream step g into its ring stage
+        const int st = (int)(g % nstage);
+        mbar_expect_tx(&s_full[st], (uint32_t)sizeof(GsRec));
+        bulk_g2s(&ring[st], &prog[g % nsteps], (uint32_t)sizeof(GsRec), &s_full[st]);
+    };
+    if (tid == 0)
+        for (long long g = 0; g < nstage - 1 && g < total; ++g) issue(g);
+    long long g = 0;
     int converged = 0;
     for (int it = 0; it < maxiter; ++it) {
-        double err = 0.0;
-        for (int lv = 0; lv < nlevels; ++lv) {
-            const int l0 = level_ptr[lv], l1 = level_ptr[lv + 1];
-            for (int t0 = l0; t0 < l1; t0 += GS_THREADS / GS_LANES) {     // (uniform trip count: shuffles below are full-warp)
-                const int t = t0 + slot;
-                const bool on = t < l1;
-                const int ip = on ? order[t] : 0;
-                double s0 = 0.0, s1 = 0.0;
-                if (on) {
-                    const double f1 = s_f[ip];
-                    const int j1 = indptr[ip + 1];
-                    for (int jp = indptr[ip] + sub; jp < j1; jp += GS_LANES) {
-                        const int ip2 = indices[jp];
-                        const double2 e01 = *reinterpret_cast<const double2*>(edge + 4 * (int64_t)jp);
-                        const double2 e23 = *reinterpret_cast<const double2*>(edge + 4 * (int64_t)jp + 2);
-                        const double df2 = -e01.x * s_y[2 * ip2] - e01.y * s_y[2 * ip2 + 1];
-                        const double num = 6 * (f1 - s_f[ip2]) - 2 * df2;
-                        s0 += num * e23.x;
-                        s1 += num * e23.y;
-                    }
-                }
+        double err = 0.0, s0 = 0.0, s1 = 0.0;
+        for (int s = 0; s < nsteps; ++s, ++g) {
+            // the stage of step g-1 was released by the barrier that ended it: refill it with step g+nstage-1
+            if (tid == 0 && g + nstage - 1 < total) issue(g + nstage - 1);
+            const int st = (int)(g % nstage);
+            mbar_wait(&s_full[st], (uint32_t)((g / nstage) & 1));
+            const GsRec& r = ring[st];
+            const int flags = r.hdr[0];
+            if (flags & 1) { s0 = 0.0; s1 = 0.0; }
+            const int ip = r.vip[slot];
+            const int ip2 = r.nb[tid];
+            if (ip2 >= 0) {
+                const double f1 = s_f[ip];
+                const double2 e01 = *reinterpret_cast<const double2*>(&r.e[tid][0]);
+                const double2 e23 = *reinterpret_cast<const double2*>(&r.e[tid][2]);
+                const double df2 = -e01.x * s_y[2 * ip2] - e01.y * s_y[2 * ip2 + 1];
+                const double num = 6 * (f1 - s_f[ip2]) - 2 * df2;
+                s0 += num * e23.x;
+                s1 += num * e23.y;
+            }
+            if (flags & 2) {                                    // (block-uniform: the shuffles are full-warp)
+                double t0 = s0, t1 = s1;
 #pragma unroll
                 for (int off = GS_LANES / 2; off > 0; off >>= 1) {
-                    s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                    t0 += __shfl_xor_sync(0xffffffffu, t0, off);
+                    t1 += __shfl_xor_sync(0xffffffffu, t1, off);
                 }
-                if (on && sub == 0) {
-                    const double2 qa = *reinterpret_cast<const double2*>(qinv + 4 * (int64_t)ip);
-                    const double2 qb = *reinterpret_cast<const double2*>(qinv + 4 * (int64_t)ip + 2);
-                    const double r0 = qa.x * s0 + qa.y * s1;
-                    const double r1 = qb.x * s0 + qb.y * s1;
+                if (ip >= 0 && sub == 0) {
+                    const double2 qa = *reinterpret_cast<const double2*>(&r.qinv[slot][0]);
+                    const double2 qb = *reinterpret_cast<const double2*>(&r.qinv[slot][2]);
+                    const double r0 = qa.x * t0 + qa.y * t1;
+                    const double r1 = qb.x * t0 + qb.y * t1;
                     double change = fmax(fabs(s_y[2 * ip] + r0), fabs(s_y[2 * ip + 1] + r1));
                     s_y[2 * ip] = -r0;
                     s_y[2 * ip + 1] = -r1;
@@ -101,7 +158,7 @@ ct_gradients_kernel(int npts, int Z, const int* __restrict__ indptr, const int* 
                     err = fmax(err, change);
                 }
             }
-            __syncthreads();
+            __syncthreads();      // the step's gradients are visible; its ring stage is free
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) err = fmax(err, __shfl_xor_sync(0xffffffffu, err, off));
@@ -115,11 +172,18 @@ ct_gradients_kernel(int npts, int Z, const int* __restrict__ indptr, const int* 
         __syncthreads();
         if (s_done) { converged = s_done; break; }
     }
+    // copies that were issued ahead but never consumed must land before the CTA may exit
+    if (tid == 0) {
+        const long long gdone = converged ? (long long)converged * nsteps : total;
+        for (long long gg = gdone; gg < gdone + nstage - 1 && gg < total; ++gg)
+            mbar_wait(&s_full[(int)(gg % nstage)], (uint32_t)((gg / nstage) & 1));
+    }
     for (int i = tid; i < npts; i += GS_THREADS) {
         grad[((int64_t)i * 2) * Z + z] = s_y[2 * i];
         grad[((int64_t)i * 2 + 1) * Z + z] = s_y[2 * i + 1];
     }
     if (tid == 0 && niter) niter[z] = converged;   // 0: not converged within maxiter (scipy warns and goes on)
+    __syncthreads();                               // (thread 0's waits above precede every thread's exit)
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -221,17 +285,22 @@ using namespace holo;
 
 extern "C" {
 
-int holo_scatter_gradients(int npts, int Z, const int* indptr, const int* indices, const double* edge,
-                           const double* qinv, const int* order, const int* level_ptr, int nlevels,
-                           const double* data, int maxiter, double tol, double* grad, int* niter, void* stream) {
-    HOLO_REQUIRE(indptr && indices && edge && qinv && order && level_ptr && data && grad, "holo_scatter_gradients: NULL argument");
-    HOLO_REQUIRE(npts > 0 && Z > 0 && nlevels > 0 && maxiter > 0, "holo_scatter_gradients: bad shape");
-    const size_t smem = sizeof(double) * 3 * (size_t)npts;
-    HOLO_REQUIRE(smem <= 220 * 1024, "holo_scatter_gradients: too many grid points for shared memory (M*Q <= 9386)");
-    if (smem > 48 * 1024)
-        HOLO_CUDA(cudaFuncSetAttribute(ct_gradients_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ct_gradients_kernel<<<Z, GS_THREADS, smem, (cudaStream_t)stream>>>(npts, Z, indptr, indices, edge, qinv, order, level_ptr,
-                                                                        nlevels, data, maxiter, tol, grad, niter);
+int holo_scatter_step_bytes(void) { return (int)sizeof(GsRec); }
+
+int holo_scatter_gradients(int npts, int Z, const void* program, int nsteps, const double* data, int maxiter, double tol,
+                           double* grad, int* niter, void* stream) {
+    HOLO_REQUIRE(program && data && grad, "holo_scatter_gradients: NULL argument");
+    HOLO_REQUIRE(npts > 0 && Z > 0 && nsteps > 0 && maxiter > 0, "holo_scatter_gradients: bad shape");
+    HOLO_REQUIRE((reinterpret_cast<uintptr_t>(program) & 15) == 0, "holo_scatter_gradients: program must be 16-byte aligned");
+    // the deepest step ring that still fits next to the slice's data and gradients
+    const size_t fixed = sizeof(double) * 3 * (size_t)npts;
+    int nstage = GS_MAX_STAGE;
+    while (nstage > 2 && fixed + (size_t)nstage * sizeof(GsRec) > 226 * 1024) --nstage;
+    const size_t smem = fixed + (size_t)nstage * sizeof(GsRec);
+    HOLO_REQUIRE(smem <= 226 * 1024, "holo_scatter_gradients: too many grid points for shared memory (M*Q <= 8700)");
+    HOLO_CUDA(cudaFuncSetAttribute(ct_gradients_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ct_gradients_kernel<<<Z, GS_THREADS, smem, (cudaStream_t)stream>>>(npts, Z, (const GsRec*)program, nsteps, nstage, data, maxiter,
+                                                                        tol, grad, niter);
     holo::count_launches(1);
     return holo_check_launch("holo_scatter_gradients");
 }

@@ -256,19 +256,17 @@ class Semi_Analytic_Model:
         log.debug(f"mmbulge scatter = {scatter}")
         if scatter > 0.0:
             log.info(f"Adding MMbulge scatter ({scatter:.4e})")
-            dur = datetime.now()
             mass_bef = self._integrated_binary_density_device(dens)
             self._dens_bef_dev = dens
-            dens = add_scatter_to_masses(self.mtot, self.mrat, dens, scatter, log=log)     # device (K6)
+            pending = []
+            dens = add_scatter_to_masses(self.mtot, self.mrat, dens, scatter, log=log, _defer_check=pending)   # device (K6)
+            self._scatter_flags_dev = pending[0]
             self._dens_aft_dev = dens.clone() if has_gmt else dens    # (the stalled bins are zeroed in place below)
             mass_aft = self._integrated_binary_density_device(dens)
-            dur = datetime.now() - dur
-            dm = (mass_aft - mass_bef) / mass_bef
-            log.info(f"Scatter added after {dur.total_seconds()} sec")
-            msg = f"mass: {mass_bef:.2e} ==> {mass_aft:.2e} || change = {dm:.4e}"
-            log.info(f"\t{msg}")
-            if np.fabs(dm) > 0.2:
-                log.error(f"Warning, significant change in number-mass!  {msg}")
+            # The reference logs the change of the integrated number here (sam.py:381-389).  The two integrals stay on
+            # the device: reading them back now would stall the launch queue twice per SAM; the message is emitted
+            # the next time the host looks at this model's results anyway (`_report_scatter_mass`).
+            self._scatter_mass_dev = (mass_bef, mass_aft)
 
         # set values after redshift zero to have zero density   (sam.py:392-394)
         if has_gmt:
@@ -281,6 +279,23 @@ class Semi_Analytic_Model:
             self._compute_density()
         return self._density_dev
 
+    def _report_scatter_mass(self):
+        """Deferred log of the change of the integrated number by the M-Mbulge scatter (``sam.py:381-389``)."""
+        pair = getattr(self, "_scatter_mass_dev", None)
+        if pair is None:
+            return
+        self._scatter_mass_dev = None
+        flags = getattr(self, "_scatter_flags_dev", None)
+        if flags is not None and int(flags.item()) != 0:
+            from holodeck_b200.sams.scatter import _bad_values_error
+            raise _bad_values_error(self._log)                # sam.py:1376-1380
+        mass_bef, mass_aft = (float(vv.item()) for vv in pair)
+        dm = (mass_aft - mass_bef) / mass_bef
+        msg = f"mass: {mass_bef:.2e} ==> {mass_aft:.2e} || change = {dm:.4e}"
+        self._log.info(f"Scatter added\t{msg}")
+        if np.fabs(dm) > 0.2:
+            self._log.error(f"Warning, significant change in number-mass!  {msg}")
+
     @property
     def static_binary_density(self):
         """Number-density of binaries d^3 n / [dlog10(M) dq dz] in [Mpc^-3], shape (M, Q, Z).
@@ -289,6 +304,7 @@ class Semi_Analytic_Model:
         """
         if self._density_host is None:
             self._density_host = _lib.to_host(self._static_binary_density_device())
+            self._report_scatter_mass()
         return self._density_host
 
     @property
@@ -321,7 +337,7 @@ class Semi_Analytic_Model:
         integ = torch.trapezoid(dens, _lib.to_dev(np.log10(self.mtot)), dim=0)
         integ = torch.trapezoid(integ, _lib.to_dev(self.mrat), dim=0)
         integ = torch.trapezoid(integ, _lib.to_dev(self.redz), dim=0)
-        return float(integ.item())
+        return integ                      # 0-d device tensor
 
     @property
     def _dens_bef(self):
@@ -451,6 +467,7 @@ class Semi_Analytic_Model:
                                               params=params, seed=seed, r0=r0, device=device, _precomputed=strain)
         hc_ss = ret_vals[0]
         hc_bg = ret_vals[1]
+        self._report_scatter_mass()        # (the draws have synchronised: reading two scalars back is free now)
         if params:
             return hc_ss, hc_bg, ret_vals[2], ret_vals[3]
         return hc_ss, hc_bg

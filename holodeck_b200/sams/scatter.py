@@ -77,6 +77,45 @@ def _dependency_levels(indptr, indices, npts):
     return order, level_ptr
 
 
+GS_THREADS, GS_LANES = 256, 8
+GS_SLOTS = GS_THREADS // GS_LANES
+#: one step of the Gauss-Seidel step program, byte for byte the `GsRec` of csrc/holo_scatter.cu
+_STEP_DTYPE = np.dtype([("e", "f8", (GS_THREADS, 4)), ("qinv", "f8", (GS_SLOTS, 4)), ("nb", "i4", GS_THREADS),
+                        ("vip", "i4", GS_SLOTS), ("hdr", "i4", 4)])
+
+
+def _step_program(indptr, indices, edge4, qinv, order, level_ptr):
+    """Flatten the level schedule of the Gauss-Seidel sweep into fixed-size step records (geometry only).
+
+    A step handles up to ``GS_SLOTS`` vertices of ONE level (``GS_LANES`` lanes each, lane ``l`` taking neighbours
+    ``l, l + 8, ...`` in scipy's neighbour order -- the summation order of the round-1 kernel); vertices with more than
+    8 neighbours (one hull corner of the named grid has 82) span several consecutive steps ("rounds"), the first
+    flagged to clear the sums, the last to apply the update.  The kernel streams these records with TMA bulk copies.
+    """
+    deg = np.diff(indptr)
+    steps = []
+    for lv in range(level_ptr.size - 1):
+        verts = order[level_ptr[lv]:level_ptr[lv + 1]]
+        for c0 in range(0, verts.size, GS_SLOTS):
+            chunk = verts[c0:c0 + GS_SLOTS]
+            rounds = max(1, -(-int(deg[chunk].max()) // GS_LANES))
+            for rr in range(rounds):
+                rec = np.zeros((), dtype=_STEP_DTYPE)
+                rec["nb"][:] = -1
+                rec["vip"][:] = -1
+                rec["vip"][:chunk.size] = chunk
+                rec["qinv"][:chunk.size] = qinv[chunk]
+                kk = rr * GS_LANES + np.arange(GS_LANES)[None, :]                 # (1, lanes) neighbour number
+                has = kk < deg[chunk][:, None]                                    # (slots, lanes)
+                jp = np.where(has, indptr[chunk][:, None] + kk, 0)
+                nb = np.where(has, indices[jp], -1)
+                rec["nb"][:chunk.size * GS_LANES] = nb.ravel()
+                rec["e"][:chunk.size * GS_LANES] = np.where(has[..., None], edge4[jp], 0.0).reshape(-1, 4)
+                rec["hdr"][0] = (1 if rr == 0 else 0) | (2 if rr == rounds - 1 else 0)
+                steps.append(rec)
+    return np.array(steps, dtype=_STEP_DTYPE)
+
+
 def scatter_geometry(mtot, mrat, refine=4):
     """Host-side, data-independent set-up for one ``(mtot, mrat)`` grid (cached by the caller)."""
     import scipy.spatial
@@ -161,8 +200,10 @@ def scatter_geometry(mtot, mrat, refine=4):
     edge4 = np.ascontiguousarray(np.stack([ex, ey, ex / L3, ey / L3], axis=1))
     det = qmat[:, 3]
     qinv = np.ascontiguousarray(np.stack([qmat[:, 2] / det, -qmat[:, 1] / det, -qmat[:, 1] / det, qmat[:, 0] / det], axis=1))
+    program = _step_program(indptr, indices, edge4, qinv, order, level_ptr)
     return dict(npts=npts, G=grid_size, mgrid_log10=mgrid_log10, points=pts, indptr=indptr, indices=indices, edge=edge,
-                qmat=qmat, edge4=edge4, qinv=qinv, order=order, level_ptr=level_ptr, geo=geo, i0=i0, i1=i1, y0=y0, y1=y1, tri=tri)
+                qmat=qmat, edge4=edge4, qinv=qinv, order=order, level_ptr=level_ptr, geo=geo, i0=i0, i1=i1, y0=y0, y1=y1, tri=tri,
+                program=program)
 
 
 def _device_geometry(mtot, mrat, refine):
@@ -173,19 +214,28 @@ def _device_geometry(mtot, mrat, refine):
         gg = scatter_geometry(mtot, mrat, refine)
         lib = _lib.load()
         assert lib.holo_scatter_geo_bytes() == _GEO_DTYPE.itemsize
-        dev = dict(npts=gg["npts"], G=gg["G"], mgrid_log10=gg["mgrid_log10"], nlevels=int(gg["level_ptr"].size - 1))
-        for name in ("indptr", "indices", "order", "level_ptr", "i0", "i1"):
+        assert lib.holo_scatter_step_bytes() == _STEP_DTYPE.itemsize
+        dev = dict(npts=gg["npts"], G=gg["G"], mgrid_log10=gg["mgrid_log10"], nsteps=int(gg["program"].size))
+        for name in ("i0", "i1"):
             dev[name] = _lib.to_dev(gg[name], dtype=torch.int32)
-        for name in ("edge4", "qinv", "y0", "y1"):
+        for name in ("y0", "y1"):
             dev[name] = _lib.to_dev(gg[name])
         dev["geo"] = torch.from_numpy(gg["geo"].view(np.uint8).copy()).to(_lib.device())
+        dev["program"] = torch.from_numpy(gg["program"].view(np.uint8).copy()).to(_lib.device())
         if len(_GEO_CACHE) > 8:
             _GEO_CACHE.clear()
         _GEO_CACHE[key] = hit = dev
     return hit
 
 
-def add_scatter_to_masses(mtot, mrat, dens, scatter, refine=4, log=None):
+def _bad_values_error(log=None):
+    err = "After 0th order interpolation, bad values remain!"        # sam.py:1376-1380
+    if log is not None:
+        log.exception(err)
+    return ValueError(err)
+
+
+def add_scatter_to_masses(mtot, mrat, dens, scatter, refine=4, log=None, *, _defer_check=None):
     """Add the given scatter [dex] to masses m1 and m2 of a ``(M, Q, Z)`` density grid (``sam.py:1291-1394``).
 
     ``dens`` may be a numpy array (numpy is returned, as the reference) or a CUDA tensor (a CUDA tensor is returned).
@@ -214,9 +264,8 @@ def add_scatter_to_masses(mtot, mrat, dens, scatter, refine=4, log=None):
 
     grad = _lib.empty((npts, 2, Z))
     niter = torch.empty(Z, dtype=torch.int32, device=data.device)
-    rc = lib.holo_scatter_gradients(npts, Z, _lib.ptr(gg["indptr"]), _lib.ptr(gg["indices"]), _lib.ptr(gg["edge4"]),
-                                    _lib.ptr(gg["qinv"]), _lib.ptr(gg["order"]), _lib.ptr(gg["level_ptr"]), gg["nlevels"],
-                                    _lib.ptr(data), 400, 1e-6, _lib.ptr(grad), _lib.ptr(niter), _lib.stream())
+    rc = lib.holo_scatter_gradients(npts, Z, _lib.ptr(gg["program"]), gg["nsteps"], _lib.ptr(data), 400, 1e-6,
+                                    _lib.ptr(grad), _lib.ptr(niter), _lib.stream())
     _lib.check(rc, "add_scatter_to_masses (gradients)")
     grid = _lib.empty((G, G, Z))
     flags = torch.zeros(1, dtype=torch.int32, device=data.device)
@@ -228,10 +277,9 @@ def add_scatter_to_masses(mtot, mrat, dens, scatter, refine=4, log=None):
     rc = lib.holo_scatter_bilinear(npts, G, Z, _lib.ptr(gg["i0"]), _lib.ptr(gg["i1"]), _lib.ptr(gg["y0"]), _lib.ptr(gg["y1"]),
                                    _lib.ptr(grid), _lib.ptr(out), _lib.stream())
     _lib.check(rc, "add_scatter_to_masses (back-interpolation)")
-    if int(flags.item()) != 0:
-        err = "After 0th order interpolation, bad values remain!"        # sam.py:1376-1380
-        if log is not None:
-            log.exception(err)
-        raise ValueError(err)
+    if _defer_check is not None:
+        _defer_check.append(flags)      # the caller reads the flag at its next synchronisation point (no stall here)
+    elif int(flags.item()) != 0:
+        raise _bad_values_error(log)
     out = out.reshape(M, Q, Z)
     return out if on_dev else _lib.to_host(out)

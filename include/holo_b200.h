@@ -335,13 +335,15 @@ int holo_model_details_hist(const double* redz_edges /* (Z,) */, const double* r
 
 /* gradients at the triangulation vertices: scipy interpnd `_estimate_gradients_2d_global` (Gauss-Seidel,
  * maxiter / tol as CloughTocher2DInterpolator: 400, 1e-6), all Z slices at once.
- * indptr/indices: Delaunay.vertex_neighbor_vertices; edge (nnz,4): ex, ey, ex/L^3, ey/L^3 per directed edge;
- * qinv (npts,4): inverse of the vertex's 2x2 normal matrix; order/level_ptr: vertices grouped by dependency level.
- * niter (Z,) (may be NULL): sweeps used, 0 = not converged. */
-int holo_scatter_gradients(int npts, int Z, const int* indptr, const int* indices, const double* edge,
-                           const double* qinv, const int* order, const int* level_ptr, int nlevels,
-                           const double* data, int maxiter, double tol, double* grad, int* niter,
-                           void* stream);
+ * `program` (16-byte aligned, nsteps records of holo_scatter_step_bytes() bytes): the level schedule of the sweep
+ * flattened by the host into one fixed-size record per step -- per thread (8 lanes per vertex, 32 vertices per step)
+ * the neighbour vertex and ex, ey, ex/L^3, ey/L^3 of the edge (Delaunay.vertex_neighbor_vertices order), per vertex
+ * slot the vertex and the inverse of its 2x2 normal matrix, and a header word (bit 0: first round of the step's
+ * vertices, bit 1: last round).  The kernel streams the records through shared memory with TMA bulk copies
+ * (cp.async.bulk + mbarrier).  niter (Z,) (may be NULL): sweeps used, 0 = not converged. */
+int holo_scatter_step_bytes(void);
+int holo_scatter_gradients(int npts, int Z, const void* program, int nsteps, const double* data, int maxiter,
+                           double tol, double* grad, int* niter, void* stream);
 
 /* Clough-Tocher values at `ngrid` regular-grid points (geometry records of holo_scatter_geo_bytes() bytes
  * each: simplex, nearest vertex, vertices, barycentric coordinates, edge vectors, g[3]); NaN (outside the
