@@ -30,8 +30,8 @@ def tm(fn, n=3):
         a.record(); r = fn(); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
     return best, r
 grad = _lib.empty((npts, 2, Z)); niter = torch.empty(Z, dtype=torch.int32, device="cuda")
-t, _ = tm(lambda: lib.holo_scatter_gradients(npts, Z, _lib.ptr(gg["indptr"]), _lib.ptr(gg["indices"]), _lib.ptr(gg["edge4"]), _lib.ptr(gg["qinv"]), _lib.ptr(gg["order"]), _lib.ptr(gg["level_ptr"]), gg["nlevels"], _lib.ptr(data), 400, 1e-6, _lib.ptr(grad), _lib.ptr(niter), _lib.stream()))
-print("K6a gradients: %.2f ms  (levels %d, sweeps max %d)" % (t, gg["nlevels"], int(niter.max())))
+t, _ = tm(lambda: lib.holo_scatter_gradients(npts, Z, _lib.ptr(gg["program"]), gg["nsteps"], _lib.ptr(data), 400, 1e-6, _lib.ptr(grad), _lib.ptr(niter), _lib.stream()))
+print("K6a gradients: %.2f ms  (steps %d, sweeps max %d)" % (t, gg["nsteps"], int(niter.max())))
 grid = _lib.empty((G, G, Z)); flags = torch.zeros(1, dtype=torch.int32, device="cuda")
 t, _ = tm(lambda: lib.holo_scatter_ct_eval(G*G, Z, _lib.ptr(gg["geo"]), _lib.ptr(data), _lib.ptr(grad), _lib.ptr(grid), _lib.ptr(flags), _lib.stream()))
 print("K6b CT eval + fill: %.2f ms" % t)
