@@ -57,8 +57,14 @@ constexpr int FGROUP = 4;            // frequencies per CTA (4 doubles = one 32 
 __host__ __device__ constexpr int pool_entries_of(int variant) {
     return (variant == HOLO_LOUDEST_PLAIN || variant == HOLO_LOUDEST_PAR || variant == HOLO_LOUDEST_PAR_REDZ) ? 10240 : 6144;
 }
-constexpr int GROUP_RESERVE = 288;   // head of the pool: CDF table of the pass's superposition group
-constexpr double GROUP_MAX_LAM = 0.25;   // elements below this expectation value are drawn as one Poisson process
+#ifndef HOLO_GROUP_RESERVE
+#define HOLO_GROUP_RESERVE 288
+#endif
+constexpr int GROUP_RESERVE = HOLO_GROUP_RESERVE;   // head of the pool: CDF table of the pass's superposition group
+#ifndef HOLO_GROUP_MAX_LAM
+#define HOLO_GROUP_MAX_LAM 0.25
+#endif
+constexpr double GROUP_MAX_LAM = HOLO_GROUP_MAX_LAM;   // elements below this expectation value are drawn as one Poisson process
 constexpr int CLS_GROUP = 6;         // (continues the CLS_* enum of holo_rng.cuh) member of the superposition group
 constexpr int STREAM_GWB = 1, STREAM_LOUD = 2, STREAM_SSBG = 3, STREAM_BULK = 4;
 static_assert(FGROUP * (TABLE_WMAX + 2) + GROUP_RESERVE <= pool_entries_of(0), "one cell must always fit the table pool");
@@ -603,7 +609,17 @@ realize_kernel(RealizeArgs a) {
                     const int i = base + lane;
                     const bool is = (i < nmain) && (((s_rec[i].meta >> 2) & 7u) == CLS_PTRS);
                     const unsigned bal = __ballot_sync(0xffffffffu, is);
-                    if (is) s_plist[np + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)i;
+                    if (is) {
+                        const int j = np + __popc(bal & ((1u << lane) - 1u));
+                        s_plist[j] = (unsigned short)i;
+                        // set-up of the transformed rejection shared by all realizations (prep_draw's a0, a1): b goes
+                        // to the free tail of s_gcum (group members fill it from the front, and ngrp + nmain <= NREC),
+                        // vr into the record's unused table fields
+                        FPrep pp;
+                        prep_draw(s_rec[i].lam, a.thresh, pp);
+                        s_gcum[NREC - 1 - j] = pp.a0;
+                        *reinterpret_cast<double*>(&s_rec[i].kmin) = pp.a1;
+                    }
                     np += __popc(bal);
                 }
                 if (lane == 0) s_np = np;
@@ -690,7 +706,160 @@ realize_kernel(RealizeArgs a) {
         // The two divergent stages take the slots one after the other in a run-time loop (one copy of the code);
         // their sums go through `tacc` and are merged into the slot's accumulators with static register indices.
         const int np = s_np;
-        if (ngrp > 0 || np > 0) {
+        if constexpr (SACC && RPT > 1) {
+            // ---- All RPT slots of a thread advance through the two divergent stages in LOCK-STEP, as in phase A: the
+            //      Philox blocks, the searches and the proposals of the slots are independent dependency chains the
+            //      scheduler can interleave (taken one slot after the other these stages ran at 39 % issue-slot use and
+            //      held 23 % of a CTA's cycles).  Every slot draws exactly the random numbers it drew before.
+            bool live[RPT];
+            DrawKey kk[RPT];
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+                live[u] = (r_first + u * THREADS) < Rtot;
+                set_key(u);
+                kk[u] = key;
+            }
+            if (ngrp > 0 && live[0]) {
+                // the superposition group: one Poisson process of rate Lambda = sum lam_k per slot; each of its events
+                // belongs to member k with probability lam_k / Lambda (see draw_group in holo_rng.cuh)
+                const int gk = s_gspec[0], gW = s_gspec[1], glg = s_gspec[2];
+                uint32_t w0[RPT], w1[RPT], qq[RPT];
+#pragma unroll
+                for (int u = 0; u < RPT; ++u) {
+                    const Philox4 gb = philox4x32_10(pass_id, fgk | ((uint32_t)PURPOSE_PASS_COUNT << 28), kk[u].real,
+                                                     kk[u].stream << 24, kk[u].k0, kk[u].k1);
+                    w0[u] = gb.v[0];
+                    w1[u] = gb.v[1];
+                }
+                table_ladder_n<RPT>(s_pool, 1u, gW, glg, w0, qq);
+                int nev[RPT], nmax = 0;
+#pragma unroll
+                for (int u = 0; u < RPT; ++u) {
+                    double ne = (double)(gk + (int)(qq[u] - 1u));
+                    if (table_ambiguous(s_pool, 1u, gW, qq[u], w0[u]))
+                        ne = table_resolve(glam_tot, s_pool + 1, gk, gW, (int)(qq[u] - 1u), w0[u], w1[u]);
+                    nev[u] = live[u] ? (int)ne : 0;
+                    nmax = nev[u] > nmax ? nev[u] : nmax;
+                }
+                // events of HEAD members are parked (six 10-bit record indices per 64-bit word) and appended to the
+                // buckets outside the event loop (see the single-slot form below)
+                unsigned long long pend[RPT];
+                int npend[RPT];
+#pragma unroll
+                for (int u = 0; u < RPT; ++u) { pend[u] = 0ull; npend[u] = 0; }
+                uint32_t odd2[RPT], odd3[RPT];          // words 2, 3 of the current pick block: the odd event's uniform
+                for (int ev = 0; ev < nmax; ++ev) {
+                    double v[RPT];
+                    if ((ev & 1) == 0) {
+#pragma unroll
+                        for (int u = 0; u < RPT; ++u) {
+                            const Philox4 pb = philox4x32_10(pass_id, fgk | ((uint32_t)PURPOSE_PASS_PICK << 28), kk[u].real,
+                                                             (kk[u].stream << 24) | (uint32_t)(ev >> 1), kk[u].k0, kk[u].k1);
+                            v[u] = u53(pb.v[0], pb.v[1]) * glam_tot;
+                            odd2[u] = pb.v[2];
+                            odd3[u] = pb.v[3];
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < RPT; ++u) v[u] = u53(odd2[u], odd3[u]) * glam_tot;
+                    }
+                    int base[RPT];
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) base[u] = 0;
+                    int len = ngrp;                     // member index = #{j : gcum[j] <= v}: one loop for all slots
+                    while (len > 1) {
+                        const int half = len >> 1;
+#pragma unroll
+                        for (int u = 0; u < RPT; ++u)
+                            if (s_gcum[base[u] + half - 1] <= v[u]) base[u] += half;
+                        len -= half;
+                    }
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) {
+                        if (s_gcum[base[u]] <= v[u] && base[u] < ngrp - 1) base[u] += 1;
+                        if (ev < nev[u]) {
+                            const int slot = NREC - 1 - base[u];
+                            const Rec rec = s_rec[slot];
+                            const bool gslot = is_gslot(u);
+                            if (has_events(VARIANT) && (rec.meta & META_HEAD) && !gslot) {
+                                if (npend[u] == 6) {
+                                    const int r = r_first + u * THREADS;
+                                    while (npend[u] > 0) {
+                                        const Rec pr = s_rec[(int)(pend[u] & 1023ull)];
+                                        push_event(a, f0 + (int)(pr.meta & 3u), r, pr.cell, 1.0);
+                                        pend[u] >>= 10;
+                                        --npend[u];
+                                    }
+                                }
+                                pend[u] = (pend[u] << 10) | (unsigned long long)slot;
+                                ++npend[u];
+                            } else {
+                                fold_sacc<VARIANT>(a, rec, f0, r_first + u * THREADS, 1.0, &s_acc[0][SACC ? u : 0][SACC ? tid : 0],
+                                                   SACC_STRIDE, gslot);
+                            }
+                        }
+                    }
+                }
+                if (has_events(VARIANT)) {
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) {
+                        const int r = r_first + u * THREADS;
+                        while (npend[u] > 0) {
+                            const Rec pr = s_rec[(int)(pend[u] & 1023ull)];
+                            push_event(a, f0 + (int)(pr.meta & 3u), r, pr.cell, 1.0);
+                            pend[u] >>= 10;
+                            --npend[u];
+                        }
+                    }
+                }
+            }
+            // ---- PTRS list: every slot walks it at its own pace (a rejected proposal delays only its own slot of its
+            //      own lane), but the proposals of the RPT slots -- a Philox block and twenty flops each -- are
+            //      computed side by side; only the rare undecided ones take the out-of-line exact test
+            if (np > 0 && live[0]) {
+                int it[RPT];
+                uint32_t trial[RPT];
+#pragma unroll
+                for (int u = 0; u < RPT; ++u) { it[u] = live[u] ? 0 : np; trial[u] = 0u; }
+                for (;;) {
+                    bool any = false;
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) any |= (it[u] < np);
+                    if (!any) break;
+                    double kq[RPT], usq[RPT], Vq[RPT];
+                    int dec[RPT], ri[RPT];
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) {
+                        const int j = it[u] < np ? it[u] : np - 1;          // (finished slots compute a discarded proposal)
+                        ri[u] = s_plist[j];
+                        const double lam = s_rec[ri[u]].lam;
+                        const uint32_t meta = s_rec[ri[u]].meta;
+                        const double b = s_gcum[NREC - 1 - j];
+                        const double vr = *reinterpret_cast<const double*>(&s_rec[ri[u]].kmin);
+                        const uint64_t idx = (uint64_t)(uint32_t)s_rec[ri[u]].cell * (uint64_t)a.F_key +
+                                             (uint64_t)(a.f_key0 + f0 + (int)(meta & 3u));
+                        dec[u] = ptrs_propose(lam, b, vr, element_bits(kk[u], idx, trial[u]), &kq[u], &usq[u], &Vq[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) {
+                        if (it[u] >= np) continue;
+                        bool ok = dec[u] > 0;
+                        if (dec[u] == 0) {
+                            const int j = it[u];
+                            ok = ptrs_decide(s_rec[ri[u]].lam, s_gcum[NREC - 1 - j], usq[u], Vq[u], kq[u]);
+                        }
+                        if (ok) {
+                            fold_sacc<VARIANT>(a, s_rec[ri[u]], f0, r_first + u * THREADS, kq[u], &s_acc[0][SACC ? u : 0][SACC ? tid : 0],
+                                               SACC_STRIDE, is_gslot(u));
+                            ++it[u];
+                            trial[u] = 0u;
+                        } else {
+                            ++trial[u];
+                        }
+                    }
+                }
+            }
+        } else if (ngrp > 0 || np > 0) {
 #pragma unroll 1
             for (int u = 0; u < RPT; ++u) {
                 const int r = r_first + u * (int)blockDim.x;

@@ -336,6 +336,32 @@ HOLO_HD bool ptrs_trial(const FPrep& p, const Philox4& bits, double* kout) {
     return ptrs_accept(lam, inv_lam, a, b, us, V, k);
 }
 
+// The same trial in two parts, for callers that advance several independent draws in lock-step: the straight-line
+// part (proposal k and the two cheap tests, numpy's squeeze steps) and the rarely needed exact acceptance test.
+// `ptrs_propose` returns +1 accept, -1 reject, 0 undecided; the outcome of a trial is the same as `ptrs_trial`'s.
+HOLO_HD int ptrs_propose(double lam, double b, double vr, const Philox4& bits, double* kout, double* us_out, double* V_out) {
+    const double a = -0.059 + 0.02483 * b;
+    const double U = u53(bits.v[0], bits.v[1]) - 0.5;
+    const double V = u53(bits.v[2], bits.v[3]);
+    const double us = 0.5 - fabs(U);
+    double rus = (double)(1.0f / (float)us);
+    rus = rus * (2.0 - us * rus);
+    rus = rus * (2.0 - us * rus);
+    const double k = floor((2.0 * a * rus + b) * U + lam + 0.43);
+    *kout = k;
+    *us_out = us;
+    *V_out = V;
+    if ((us >= 0.07) && (V <= vr)) return 1;
+    if ((k < 0.0) || ((us < 0.013) && (V > us))) return -1;
+    return 0;
+}
+HOLO_NOINLINE_STATIC bool ptrs_decide(double lam, double b, double us, double V, double k) {
+    const double a = -0.059 + 0.02483 * b, inv_lam = 1.0 / lam;
+    const int scr = ptrs_screen(lam, inv_lam, a, b, us, V, k);
+    if (scr != 0) return scr > 0;
+    return ptrs_accept(lam, inv_lam, a, b, us, V, k);
+}
+
 HOLO_HD double draw_ptrs(const FPrep& p, const DrawKey& key, uint64_t idx) {
     for (uint32_t trial = 0; trial < 4096u; ++trial) {
         double k;
@@ -347,8 +373,14 @@ HOLO_HD double draw_ptrs(const FPrep& p, const DrawKey& key, uint64_t idx) {
 // ---- TABLE class ----------------------------------------------------------------------------------
 // Window of the tabulated CDF: below kmin the Poisson mass is < 2^-64 (lighter than the normal tail at
 // -9.5 sd), above kmin+W-1 it is ~1e-10: draws that land there take the exact slow path.
-constexpr double TABLE_MAX_LAM = 4000.0;
-constexpr int TABLE_WMAX = 1024;    // >= table_spec(TABLE_MAX_LAM).W
+#ifndef HOLO_TABLE_MAX_LAM
+#define HOLO_TABLE_MAX_LAM 4000.0
+#endif
+constexpr double TABLE_MAX_LAM = HOLO_TABLE_MAX_LAM;
+#ifndef HOLO_TABLE_WMAX
+#define HOLO_TABLE_WMAX 1024
+#endif
+constexpr int TABLE_WMAX = HOLO_TABLE_WMAX;    // >= table_spec(TABLE_MAX_LAM).W
 
 struct TableSpec {
     int kmin, W;

@@ -403,6 +403,21 @@ class Semi_Analytic_Model:
         edges, redz_final, strain = self._number_and_strain(fobs_gw_edges, hard, params=False)
         return gravwaves._gws_from_hc2(strain["h2fdf"], strain["number"], realize, True, seed, 0, False)
 
+    def gwb_old(self, fobs_gw_edges, hard=None, realize=100, *, seed=None):
+        """GWB through ``dynamic_binary_number_at_fobs`` + per-axis trapezoids (``sam.py:815-835``); returns hc (F, R).
+
+        The reference integrates ``dnum`` with three successive ``utils.trapz`` calls (``utils.py:1340-1373``) and
+        multiplies by ``diff(ln fobs_gw_edges)``: the product of the three one-dimensional trapezoid rules is the
+        8-corner mean times the bin volume that ``integrate_differential_number_3dx1d`` (K2) evaluates in one pass, and
+        ``diff(ln f_gw) == diff(ln f_orb)``; the two agree to rounding (1e-15), so this is the ``gwb_new`` device
+        path under the reference's older name.  ``hard`` may be a class (the reference's default is the class
+        ``Hard_GW``) or an instance."""
+        if hard is None:
+            hard = holo.hardening.Hard_GW
+        if isinstance(hard, type):
+            hard = hard()
+        return self.gwb_new(np.atleast_1d(fobs_gw_edges), hard=hard, realize=realize, seed=seed)
+
     def gwb_ideal(self, fobs_gw, sum=True, redz_prime=None):
         """Idealized, continuous GWB amplitude, [Phinney2001]_ Eq.5 (``sam.py:837-870``; host)."""
         from holodeck_b200 import gravwaves
