@@ -495,6 +495,7 @@ def run_b200(args):
 
     # ---- per-stage device times (CUDA events on the launching stream), one extra profiled pass
     stages = stage_times(args, fobs_edges, R, L, seed, r0)
+    shim = shim_boundary_times(args, fobs_edges, R, L, seed) if (rank == 0 and world == 1) else None
 
     if rank != 0:
         if world > 1:
@@ -587,6 +588,7 @@ def run_b200(args):
                            "note": "librarian.run_model on the same grid: nreals=100, nloudest=5, params + gwb (one sample "
                                    "per rank at a time; BASELINE configs[4] shards 2000 such samples over the ranks)"},
         "roofline": roofline,
+        "e2e_shim": shim,
         "stages_ms": {kk: round(vv, 4) for kk, vv in stages.items()},
         "kernels": per_kernel,
     }
@@ -617,6 +619,64 @@ def run_b200(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def shim_boundary_times(args, fobs_edges, R, L, seed, reps=3):
+    """The drop-in boundary SURVEY section 8(b) defines, timed as stock holodeck would use it after the
+    `sys.modules` aliasing of INTEGRATION.md section 3: the three native calls of `sam.gwb` made through the shim
+    modules with HOST numpy arrays in and out -- every call uploads its inputs and reads its full-size outputs back
+    (2 x 238 MB out of `dynamic_binary_number_at_fobs`, 238 MB in / 230 MB out of `integrate_differential_number_3dx1d`,
+    2 x 230 MB into `loudest_hc_from_sorted`), pinned read-backs, wall clock around each call.  The Python glue between
+    the calls (strain, argsort: numpy in the reference) is NOT timed here; it is prepared on the device, untimed."""
+    import torch
+    from holodeck_b200 import _lib, gravwaves, cosmo, utils, cyutils
+    from holodeck_b200.sams import sam_cyutils
+    sam, hard = make_models(args)
+    sam._static_binary_density_device()
+    fobs_cents = utils.midpoints(fobs_edges)
+    edges = [sam.mtot, sam.mrat, sam.redz, fobs_edges / 2.0]
+    best = {}
+    traffic = {}
+
+    def timed_call(name, cur, moved, fn):
+        h0, d0 = _lib.TRAFFIC["h2d"], _lib.TRAFFIC["d2h"]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        cur[name] = time.perf_counter() - t0
+        moved["h2d_bytes"] += _lib.TRAFFIC["h2d"] - h0
+        moved["d2h_bytes"] += _lib.TRAFFIC["d2h"] - d0
+        return out
+
+    for rep in range(reps + 1):
+        cur, moved = {}, {"h2d_bytes": 0, "d2h_bytes": 0}
+        redz_final, diff_num = timed_call("dynamic_binary_number_at_fobs", cur, moved, lambda: sam_cyutils.dynamic_binary_number_at_fobs(
+            fobs_cents / 2.0, sam, hard, cosmo))
+        number = timed_call("integrate_differential_number_3dx1d", cur, moved,
+                            lambda: sam_cyutils.integrate_differential_number_3dx1d(edges, diff_num))
+        assert isinstance(redz_final, np.ndarray) and isinstance(number, np.ndarray)
+        # glue (untimed): strain and rank order, as host arrays -- what the reference's numpy code hands to cyutils
+        strain = gravwaves._char_strain_sq(edges, _lib.to_dev(redz_final), params=False)
+        h2fdf = _lib.to_host(strain["h2fdf"])
+        order = torch.sort(-strain["h2fdf"][..., 0].reshape(-1), stable=True).indices.cpu().numpy()
+        msort, qsort, zsort = np.unravel_index(order, number.shape[:3])
+        del strain
+        hc2ss, hc2bg = timed_call("loudest_hc_from_sorted", cur, moved,
+                                  lambda: cyutils.loudest_hc_from_sorted(number, h2fdf, R, L, msort, qsort, zsort, seed=seed))
+        assert isinstance(hc2ss, np.ndarray) and hc2ss.shape == (args.nfreqs, R, L) and np.all(hc2bg > 0)
+        del redz_final, diff_num, number, h2fdf
+        if rep == 0:
+            continue                         # first pass: pinned blocks are allocated, caches warm up
+        traffic = {kk: int(vv) for kk, vv in moved.items()}
+        for kk, vv in cur.items():
+            best[kk] = min(best.get(kk, 1e30), vv)
+    total = sum(best.values())
+    M, Q, Z = args.shape
+    ncell = (M - 1) * (Q - 1) * (Z - 1) * args.nfreqs
+    return {"ms": {kk: round(1e3 * vv, 3) for kk, vv in best.items()}, "ms_total": round(1e3 * total, 3),
+            "value": ncell * R / total, "unit": UNIT, **traffic,
+            "note": "the three native calls of sam.gwb through the shim modules, numpy in / numpy out at full size "
+                    "(INTEGRATION.md section 3); wall clock per call, best of %d" % reps}
 
 
 def stage_times(args, fobs_edges, R, L, seed, r0):

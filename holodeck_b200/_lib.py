@@ -318,9 +318,23 @@ def empty(shape, dtype=None, dev=None):
 TRAFFIC = {"h2d": 0, "d2h": 0}
 
 
+#: device-to-host copies of at least this many bytes land in page-locked memory (torch's caching host allocator
+#: recycles the blocks): the drop-in shims hand 230 MB grids back to numpy callers, and a pageable read-back runs
+#: at a fraction of the PCIe rate
+PINNED_D2H_MIN_BYTES = 1 << 20
+
+
 def to_host(tensor):
     """CUDA tensor -> numpy array (counted device-to-host copy)."""
-    TRAFFIC["d2h"] += tensor.numel() * tensor.element_size()
+    import torch
+    nbytes = tensor.numel() * tensor.element_size()
+    TRAFFIC["d2h"] += nbytes
+    if nbytes >= PINNED_D2H_MIN_BYTES and tensor.is_cuda:
+        src = tensor.contiguous()
+        out = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+        out.copy_(src, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out.numpy()             # (the array keeps the pinned block alive; it returns to the cache with it)
     return tensor.cpu().numpy()
 
 

@@ -16,7 +16,10 @@ re-attempted on the next run (``gen_lib.py:287-319``); more than ``MAX_FAILURES`
 final barrier rank 0 combines the library into the reference's single file (``gen_lib.py:228-231``).
 """
 import argparse
+import concurrent.futures
 import json
+import queue
+import threading
 from datetime import datetime
 from pathlib import Path
 
@@ -110,10 +113,14 @@ def _check_config(output, config, resume_ok=True):
 
 def run_library(space, output, nreals=DEF_NUM_REALS, nfreqs=DEF_NUM_FBINS, nloudest=DEF_NUM_LOUDEST,
                 pta_dur=DEF_PTA_DUR, gwb_flag=True, ss_flag=True, params_flag=False, recreate=False, seed=None,
-                log=None, indices=None, streaming=True, sim_files=False, param_space_name=None):
+                log=None, indices=None, streaming=True, sim_files=False, param_space_name=None, workers=2):
     """Generate this rank's share of the library; returns ``(num_done, failures)``.
 
-    ``seed`` must be the same on every rank (``main`` broadcasts it): it fixes the sample permutation."""
+    ``seed`` must be the same on every rank (``main`` broadcasts it): it fixes the sample permutation.
+    ``workers``: host threads per rank, each driving its own CUDA stream.  A sample is ~10 ms of kernels plus a few
+    ms of host work (model construction, launches, the overflow check of the loudest split, which synchronises);
+    with two samples in flight the host work of one hides behind the kernels of the other and the kernels of the
+    two streams fill each other's tails.  Results do not depend on it (every sample has its own seed)."""
     from holodeck_b200 import utils
     from holodeck_b200.constants import YR
     rank, size = dist.world()
@@ -154,22 +161,57 @@ def run_library(space, output, nreals=DEF_NUM_REALS, nfreqs=DEF_NUM_FBINS, nloud
                 _save_npz(args, space, pnum, space.param_dict(int(pnum)), full)
         writer = stream.AsyncSampleWriter(store, also_npz=npz)
     beg = datetime.now()
-    failures = 0
-    num_done = 0
-    try:
-        for sim_num in indices:
-            params = space.param_dict(int(sim_num))
-            rv, _ = run_sam_at_pspace_params(args, space, int(sim_num), params, writer=writer)
+    state = dict(failures=0, done=0)
+    lock = threading.Lock()
+    todo = queue.SimpleQueue()
+    for sim_num in indices:
+        todo.put(int(sim_num))
+
+    def one_sample(sim_num):
+        params = space.param_dict(sim_num)
+        rv, _ = run_sam_at_pspace_params(args, space, sim_num, params, writer=writer)
+        with lock:
             if rv is False:
-                failures += 1
-            if (MAX_FAILURES is not None) and (failures > MAX_FAILURES):
-                err = f"Failed {failures} times on rank:{rank}!"
+                state["failures"] += 1
+            state["done"] += 1
+            if (MAX_FAILURES is not None) and (state["failures"] > MAX_FAILURES):
+                err = f"Failed {state['failures']} times on rank:{rank}!"
                 log.exception(err)
                 raise RuntimeError(err)
-            num_done += 1
+
+    def drain(own_stream):
+        import contextlib
+        ctx = contextlib.nullcontext()
+        if own_stream:
+            import torch
+            ctx = torch.cuda.stream(torch.cuda.Stream())
+        with ctx:
+            while True:
+                try:
+                    sim_num = todo.get_nowait()
+                except queue.Empty:
+                    return
+                one_sample(sim_num)
+
+    nworkers = max(1, int(workers))
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            nworkers = 1
+    except Exception:   # noqa: BLE001
+        nworkers = 1
+    try:
+        if nworkers > 1 and not todo.empty():
+            one_sample(todo.get_nowait())          # the first sample fills the per-grid caches (geometry, tables) once
+            with concurrent.futures.ThreadPoolExecutor(nworkers) as pool:
+                for fut in [pool.submit(drain, True) for _ in range(nworkers)]:
+                    fut.result()
+        else:
+            drain(False)
     finally:
         if writer is not None:
             writer.close()
+    failures, num_done = state["failures"], state["done"]
     run_library.last_loop_s = (datetime.now() - beg).total_seconds()
     log.info(f"\t{rank} done after {run_library.last_loop_s} s")
     dist.barrier()
@@ -196,6 +238,7 @@ def main(argv=None):
     ap.add_argument('--no-streaming', action='store_true', default=False,
                     help="reference file plane only: synchronous per-sample .npz, merged by sam_lib_combine")
     ap.add_argument('--no-combine', action='store_true', default=False)
+    ap.add_argument('--workers', type=int, default=2, help="host threads (CUDA streams) per rank; see run_library")
     args = ap.parse_args(argv)
     dist.init()
     rank, size = dist.world()
@@ -207,7 +250,7 @@ def main(argv=None):
                               pta_dur=args.pta_dur, gwb_flag=args.gwb_flag, ss_flag=args.ss_flag,
                               params_flag=args.params_flag, recreate=args.recreate, seed=seed,
                               streaming=not args.no_streaming, sim_files=args.sim_files or args.no_streaming,
-                              param_space_name=args.param_space)
+                              param_space_name=args.param_space, workers=args.workers)
     loop_s = dist.max_over_ranks(run_library.last_loop_s)
     print(f"rank {rank}: {done} samples, {fails} failures, sample loop {run_library.last_loop_s:.3f} s")
     if rank == 0:

@@ -271,6 +271,57 @@ def test_fullsize_loudest_supplied_counts(holo, full):
     assert rel_err(cyutils.sam_poisson_gwb(number, h2fdf, 1, counts=cg), want_gwb) < 1e-12
 
 
+def test_fullsize_drop_in_boundary_through_aliased_modules(holo, full):
+    """The boundary of SURVEY section 8(b), used the way INTEGRATION.md section 3 prescribes for a stock holodeck:
+    the two compiled modules are replaced by `sys.modules` aliases, the caller imports them under the REFERENCE's
+    names and passes / receives full-size HOST numpy arrays (duck-typed `sam`, `hard`, `cosmo` as sam_cyutils.pyx
+    reads them).  Outputs must be numpy, match the oracle, and equal the device-resident path bit for bit."""
+    import importlib
+    import time
+    import types
+    from oracle import chain, glue
+    wl, st = full
+    saved = {kk: sys.modules.get(kk) for kk in ("holodeck", "holodeck.sams", "holodeck.cyutils", "holodeck.sams.sam_cyutils")}
+    try:
+        import holodeck_b200.cyutils
+        import holodeck_b200.sams.sam_cyutils
+        pkg, sub = types.ModuleType("holodeck"), types.ModuleType("holodeck.sams")
+        pkg.__path__, sub.__path__ = [], []
+        sys.modules.update({"holodeck": pkg, "holodeck.sams": sub, "holodeck.cyutils": holodeck_b200.cyutils,
+                            "holodeck.sams.sam_cyutils": holodeck_b200.sams.sam_cyutils})
+        cy = importlib.import_module("holodeck.cyutils")                    # what `import holodeck.cyutils` resolves to
+        scy = importlib.import_module("holodeck.sams.sam_cyutils")
+        assert cy is holodeck_b200.cyutils and scy is holodeck_b200.sams.sam_cyutils
+        hard = _hard_with_norm(holo, wl["hard"], 10.0 ** st["norm_log10"])
+        tabs = _Tabs(chain.make_cosmo_tables(glue.OracleCosmo(closed_form=True)))
+        tt = {}
+        t0 = time.perf_counter()
+        rz, dn = scy.dynamic_binary_number_at_fobs(wl["fobs_cents"] / 2.0, _Sam(st, wl), hard, tabs)
+        tt["dynamic_binary_number_at_fobs"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        number = scy.integrate_differential_number_3dx1d(st["edges"], dn)
+        tt["integrate_differential_number_3dx1d"] = time.perf_counter() - t0
+        assert all(isinstance(vv, np.ndarray) for vv in (rz, dn, number))
+        assert rel_err(number, st["number"]) < 1e-9 and _count((number == 0) != (st["number"] == 0)) == 0
+        R, L, seed = 16, 3, 99
+        t0 = time.perf_counter()
+        hc2ss, hc2bg = cy.loudest_hc_from_sorted(st["number"], st["h2fdf"], R, L, st["msort"], st["qsort"], st["zsort"], seed=seed)
+        tt["loudest_hc_from_sorted"] = time.perf_counter() - t0
+        assert isinstance(hc2ss, np.ndarray) and hc2ss.shape == (40, R, L) and hc2bg.shape == (40, R)
+        print("drop-in boundary, numpy in / numpy out at full size [s]:", {kk: round(vv, 3) for kk, vv in tt.items()})
+        # the same draws with device-resident inputs (what the mirrored classes do internally)
+        from holodeck_b200 import _lib
+        dev = cy.loudest_hc_from_sorted(_lib.to_dev(st["number"]), _lib.to_dev(st["h2fdf"]), R, L, st["msort"], st["qsort"],
+                                        st["zsort"], seed=seed, device=True)
+        assert np.array_equal(dev[0].cpu().numpy(), hc2ss) and np.array_equal(dev[1].cpu().numpy(), hc2bg)
+    finally:
+        for kk, vv in saved.items():
+            if vv is None:
+                sys.modules.pop(kk, None)
+            else:
+                sys.modules[kk] = vv
+
+
 # ==================================================================================================
 # configs[0]: default Semi_Analytic_Model(shape=30) + Hard_GW, 20 PTA frequencies, realize=10
 # ==================================================================================================
