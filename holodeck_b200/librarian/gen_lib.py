@@ -113,7 +113,7 @@ def _check_config(output, config, resume_ok=True):
 
 def run_library(space, output, nreals=DEF_NUM_REALS, nfreqs=DEF_NUM_FBINS, nloudest=DEF_NUM_LOUDEST,
                 pta_dur=DEF_PTA_DUR, gwb_flag=True, ss_flag=True, params_flag=False, recreate=False, seed=None,
-                log=None, indices=None, streaming=True, sim_files=False, param_space_name=None, workers=2):
+                log=None, indices=None, streaming=True, sim_files=False, param_space_name=None, workers=1):
     """Generate this rank's share of the library; returns ``(num_done, failures)``.
 
     ``seed`` must be the same on every rank (``main`` broadcasts it): it fixes the sample permutation.
@@ -200,9 +200,12 @@ def run_library(space, output, nreals=DEF_NUM_REALS, nfreqs=DEF_NUM_FBINS, nloud
             nworkers = 1
     except Exception:   # noqa: BLE001
         nworkers = 1
+    t_first = None
     try:
-        if nworkers > 1 and not todo.empty():
+        if not todo.empty():
             one_sample(todo.get_nowait())          # the first sample fills the per-grid caches (geometry, tables) once
+            t_first = (datetime.now() - beg).total_seconds()
+        if nworkers > 1:
             with concurrent.futures.ThreadPoolExecutor(nworkers) as pool:
                 for fut in [pool.submit(drain, True) for _ in range(nworkers)]:
                     fut.result()
@@ -212,6 +215,7 @@ def run_library(space, output, nreals=DEF_NUM_REALS, nfreqs=DEF_NUM_FBINS, nloud
         if writer is not None:
             writer.close()
     failures, num_done = state["failures"], state["done"]
+    run_library.last_first_sample_s = t_first
     run_library.last_loop_s = (datetime.now() - beg).total_seconds()
     log.info(f"\t{rank} done after {run_library.last_loop_s} s")
     dist.barrier()
@@ -238,7 +242,7 @@ def main(argv=None):
     ap.add_argument('--no-streaming', action='store_true', default=False,
                     help="reference file plane only: synchronous per-sample .npz, merged by sam_lib_combine")
     ap.add_argument('--no-combine', action='store_true', default=False)
-    ap.add_argument('--workers', type=int, default=2, help="host threads (CUDA streams) per rank; see run_library")
+    ap.add_argument('--workers', type=int, default=1, help="host threads (CUDA streams) per rank; see run_library")
     args = ap.parse_args(argv)
     dist.init()
     rank, size = dist.world()
@@ -252,10 +256,14 @@ def main(argv=None):
                               streaming=not args.no_streaming, sim_files=args.sim_files or args.no_streaming,
                               param_space_name=args.param_space, workers=args.workers)
     loop_s = dist.max_over_ranks(run_library.last_loop_s)
-    print(f"rank {rank}: {done} samples, {fails} failures, sample loop {run_library.last_loop_s:.3f} s")
+    first_s = run_library.last_first_sample_s or 0.0
+    steady_s = dist.max_over_ranks(run_library.last_loop_s - first_s)
+    print(f"rank {rank}: {done} samples, {fails} failures, sample loop {run_library.last_loop_s:.3f} s "
+          f"(first sample incl. one-off set-up {first_s:.3f} s)")
     if rank == 0:
         print(f"library: {args.nsamples} samples on {size} rank(s), slowest sample loop {loop_s:.3f} s "
-              f"= {args.nsamples / loop_s:.1f} samples/s")
+              f"= {args.nsamples / loop_s:.1f} samples/s; after each rank's first sample: "
+              f"{(args.nsamples - size) / max(steady_s, 1e-9):.1f} samples/s")
         if not args.no_combine:
             beg = datetime.now()
             fname = holo.librarian.combine.sam_lib_combine(args.output, holo.log, recreate=True)

@@ -206,12 +206,58 @@ def scatter_geometry(mtot, mrat, refine=4):
                 program=program)
 
 
+#: geometry arrays kept in the on-disk cache (everything `_device_geometry` uploads)
+_DISK_KEYS = ("mgrid_log10", "geo", "program", "i0", "i1", "y0", "y1")
+
+
+def _cache_dir():
+    import os
+    from pathlib import Path
+    root = os.environ.get("HOLO_B200_CACHE")
+    return Path(root) if root else Path.home() / ".cache" / "holodeck_b200"
+
+
+def _cached_geometry(mtot, mrat, refine):
+    """`scatter_geometry` through an on-disk cache keyed by the grid.  The set-up is data-independent but costs 1.7 s
+    of host time at the named grid (scipy's point location of the 132,496 regular-grid points, 88 % of them outside
+    the hull) -- as much as a hundred library samples -- and every rank of every run of a library needs the same one.
+    ``HOLO_B200_CACHE`` moves the directory; ``HOLO_B200_CACHE=off`` disables the cache."""
+    import hashlib
+    import os
+    if os.environ.get("HOLO_B200_CACHE", "").lower() in ("off", "0", "none"):
+        return scatter_geometry(mtot, mrat, refine)
+    hh = hashlib.sha1()
+    for part in (np.ascontiguousarray(mtot, dtype=np.float64).tobytes(), np.ascontiguousarray(mrat, dtype=np.float64).tobytes(),
+                 str(int(refine)).encode(), str(_STEP_DTYPE).encode(), str(_GEO_DTYPE).encode(), b"v3"):
+        hh.update(part)
+    fname = _cache_dir() / f"scatter_geometry_{hh.hexdigest()[:20]}.npz"
+    try:
+        with np.load(fname) as dd:
+            gg = {kk: dd[kk] for kk in _DISK_KEYS}
+        gg["geo"] = gg["geo"].view(_GEO_DTYPE).reshape(-1)
+        gg["program"] = gg["program"].view(_STEP_DTYPE).reshape(-1)
+        gg["npts"] = int(np.size(mtot) * np.size(mrat))
+        gg["G"] = int(gg["mgrid_log10"].size)
+        return gg
+    except (OSError, KeyError, ValueError):
+        pass
+    gg = scatter_geometry(mtot, mrat, refine)
+    try:
+        fname.parent.mkdir(parents=True, exist_ok=True)
+        tmp = fname.with_suffix(f".{os.getpid()}.tmp.npz")
+        np.savez(tmp, **{kk: (gg[kk].view(np.uint8) if kk in ("geo", "program") else gg[kk]) for kk in _DISK_KEYS})
+        os.replace(tmp, fname)             # atomic: concurrent ranks write the same bytes
+    except OSError:
+        pass
+    return gg
+
+
 def _device_geometry(mtot, mrat, refine):
     import torch
     key = (np.asarray(mtot).tobytes(), np.asarray(mrat).tobytes(), int(refine), torch.cuda.current_device())
     hit = _GEO_CACHE.get(key)
     if hit is None:
-        gg = scatter_geometry(mtot, mrat, refine)
+        gg = _cached_geometry(mtot, mrat, refine)
         lib = _lib.load()
         assert lib.holo_scatter_geo_bytes() == _GEO_DTYPE.itemsize
         assert lib.holo_scatter_step_bytes() == _STEP_DTYPE.itemsize

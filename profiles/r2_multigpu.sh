@@ -12,10 +12,11 @@ for N in 8 2; do
 done
 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_n1.json 2> $OUT/bench_n1.err
 GL="-m holodeck_b200.librarian.gen_lib PS_Classic_Phenom_Uniform"
-rm -rf /tmp/lib1 /tmp/lib8 /tmp/lib8w1
+rm -rf /tmp/lib1 /tmp/lib8 /tmp/lib8w1 /tmp/lib1ref
+python $GL /tmp/lib1ref -n 60 -r 100 -l 5 --gwb --ss --params --seed 1 --no-streaming > $OUT/genlib_1gpu_reference_fileplane.log 2>&1
 python $GL /tmp/lib1 -n 250 -r 100 -l 5 --gwb --ss --params --seed 1 > $OUT/genlib_1gpu.log 2>&1
 $TR --nproc-per-node 8 --master-port 29520 $GL /tmp/lib8 -n 2000 -r 100 -l 5 --gwb --ss --params --seed 1 > $OUT/genlib_8gpu.log 2>&1
-$TR --nproc-per-node 8 --master-port 29521 $GL /tmp/lib8w1 -n 2000 -r 100 -l 5 --gwb --ss --params --seed 1 --workers 1 --no-combine > $OUT/genlib_8gpu_1worker.log 2>&1
+$TR --nproc-per-node 8 --master-port 29521 $GL /tmp/lib8w1 -n 2000 -r 100 -l 5 --gwb --ss --params --seed 1 --workers 2 --no-combine > $OUT/genlib_8gpu_2workers.log 2>&1
 ls -la /tmp/lib8 /tmp/lib8/library_store | head -20 >> $OUT/genlib_8gpu.log
 grep -h "library:\|combined\|rank 0" $OUT/genlib_*.log
 for f in $OUT/bench_*.json; do python - "$f" <<'PY'
