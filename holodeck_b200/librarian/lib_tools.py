@@ -20,278 +20,215 @@ from holodeck_b200.librarian import (
     DEF_NUM_FBINS, DEF_NUM_LOUDEST, DEF_NUM_REALS, DEF_PTA_DUR, PSPACE_FILE_SUFFIX, FNAME_LIBRARY_SIM_FILE,
 )
 
+#: parameter names the reference refuses (name, message) and renames (old -> (new, converter or None)),
+#: ``lib_tools.py:25-31``
 PARAM_NAMES__ERROR = []
 PARAM_NAMES_REPLACE = {
     "gsmf_phi0": ["gsmf_phi0_log10", None],
 }
 
 
-class _Param_Space(abc.ABC):
-    """Base class for generating holodeck libraries.  Defines the parameter space and settings."""
-
-    __version__ = "0.0"
-    _SAVED_ATTRIBUTES = ["sam_shape", "param_names", "_uniform_samples", "param_samples", "_nsamples", "_nparameters"]
-    DEFAULTS = {}
-
-    def __init__(self, parameters, log=None, nsamples=None, sam_shape=None, seed=None, random_state=None):
-        if log is None:
-            log = holo.log
-        log.debug(f"seed = {seed}")
-        if random_state is None:
-            np.random.seed(seed)
-            random_state = np.random.get_state()
-        else:
-            np.random.set_state(random_state)
-
-        try:
-            nparameters = len(parameters)
-            assert nparameters > 0
-        except (TypeError, AssertionError) as err:
-            log.exception("`parameters` must be a list of `_Param_Dist` subclasses!")
-            raise err
-
-        param_names = []
-        for param in parameters:
-            name = param.name
-            if not isinstance(param, _Param_Dist):
-                err = f"{name}: {param} is not a `_Param_Dist` object!"
+def _canonical(name, value=None, log=None, convert=False):
+    """Apply the reference's rename / refuse rules to one parameter name (and, with ``convert``, its value)."""
+    for bad, msg in PARAM_NAMES__ERROR:
+        if bad == name:
+            err = f"Found '{name}' in parameters: {msg}"
+            if log is not None:
                 log.exception(err)
-                raise ValueError(err)
-            for pname, msg in PARAM_NAMES__ERROR:
-                if pname == name:
-                    err = f"Found '{name}' in parameters: {msg}"
-                    log.exception(err)
-                    raise ValueError(err)
-            for pname, replace in PARAM_NAMES_REPLACE.items():
-                if pname != name:
-                    continue
-                new_name, new_func = replace
-                log.error(f"Found '{name}' in parameters, should be '{new_name}'!")
-                if new_func is None:
-                    name = new_name
-                else:
-                    err = f"CANNOT replace '{name}' ==> '{new_name}'!"
-                    log.exception(err)
-                    raise ValueError(err)
-            param_names.append(name)
-
-        if (nsamples is None) or (nparameters == 0):
-            log.info(f"{self}: {nsamples=} {nparameters=} - cannot generate parameter samples.")
-            uniform_samples = None
-            param_samples = None
-        else:
-            # strength = 1 : basic latin hypercube
-            lhc = sp.stats.qmc.LatinHypercube(d=nparameters, strength=1, seed=seed)
-            # (S, D) samples `S` and parameters `D`
-            uniform_samples = lhc.random(n=nsamples)
-            param_samples = np.zeros_like(uniform_samples)
-            for ii, param in enumerate(parameters):
-                param_samples[:, ii] = param(uniform_samples[:, ii])
-
-        self._log = log
-        self._nparameters = nparameters
-        self._nsamples = nsamples
-        self._seed = seed
-        self._random_state = random_state
-        self.sam_shape = sam_shape
-        self.param_names = param_names
-        self.param_samples = param_samples
-        self._parameters = parameters
-        self._uniform_samples = uniform_samples
-
-    def model_for_params(self, params, sam_shape=None):
-        """Construct ``(sam, hard)`` for a dict of parameter values (``lib_tools.py:156-212``)."""
-        if sam_shape is None:
-            sam_shape = self.sam_shape
-        settings = self.DEFAULTS.copy()
-        for name, value in params.items():
-            for pname, replace in PARAM_NAMES_REPLACE.items():
-                if pname != name:
-                    continue
-                new_name, new_func = replace
-                self._log.error(f"Found '{name}' in parameters, should be '{new_name}'!")
-                name = new_name
-                value = value if new_func is None else new_func(value)
-            for pname, msg in PARAM_NAMES__ERROR:
-                if pname == name:
-                    err = f"Found '{name}' in parameters: {msg}"
-                    self._log.exception(err)
-                    raise ValueError(err)
-            settings[name] = value
-        sam = self._init_sam(sam_shape, settings)
-        hard = self._init_hard(sam, settings)
-        return sam, hard
-
-    @classmethod
-    @abc.abstractmethod
-    def _init_sam(cls, sam_shape, params):
-        raise
-
-    @classmethod
-    @abc.abstractmethod
-    def _init_hard(cls, sam, params):
-        raise
-
-    def save(self, path_output):
-        """Save the generated samples and parameter-space info into a single ``.pspace.npz`` file."""
-        path_output = Path(path_output)
-        if not path_output.exists() or not path_output.is_dir():
-            err = f"save path {path_output} does not exist, or is not a directory!"
-            self._log.exception(err)
             raise ValueError(err)
-        fname = path_output.joinpath(f"{self.name}{PSPACE_FILE_SUFFIX}")
-        data = {key: getattr(self, key) for key in self._SAVED_ATTRIBUTES}
-        np.savez(fname, class_name=self.name, class_vers=self.__version__,
-                 librarian_version=holo.librarian.__version__, **data)
-        return fname
+    if name in PARAM_NAMES_REPLACE:
+        new_name, func = PARAM_NAMES_REPLACE[name]
+        if log is not None:
+            log.error(f"Found '{name}' in parameters, should be '{new_name}'!")
+        if func is not None:
+            if not convert:
+                err = f"CANNOT replace '{name}' ==> '{new_name}'!"
+                if log is not None:
+                    log.exception(err)
+                raise ValueError(err)
+            value = func(value)
+        name = new_name
+    return name, value
 
-    @classmethod
-    def from_save(cls, fname, log=None):
-        """Create a new parameter-space instance loaded from the given save file (``lib_tools.py:257-377``)."""
-        if log is None:
-            log = holo.log
-        data = np.load(fname, allow_pickle=True)
-        class_name = data['class_name'][()]
-        pspace_class = holo.librarian.param_spaces_dict.get(str(class_name), None)
-        if pspace_class is None:
-            log.warning(f"pspace file {fname} has {class_name=}, not found in `holo.param_spaces_dict`!")
-            pspace_class = cls
-        nsamples = None if data['param_samples'][()] is None else data['param_samples'].shape[0]
-        space = pspace_class(nsamples=nsamples, log=log)
-        param_names = data['param_names']
-        if not all(pl == pc for pl, pc in zip(param_names, space.param_names)):
-            err = f"Mismatch between loaded parameter names ({param_names}) and class parameter names ({space.param_names})!"
-            log.exception(err)
-            raise RuntimeError(err)
-        for key in space._SAVED_ATTRIBUTES:
-            try:
-                val = data[key][()]
-            except KeyError:
-                if key == '_nsamples':
-                    val = nsamples
-                elif key == '_nparameters':
-                    val = None if nsamples is None else data['param_samples'].shape[1]
-                else:
-                    raise
-            setattr(space, key, val)
-        return space
 
-    def param_dict(self, samp_num):
-        return {nn: pp for nn, pp in zip(self.param_names, self.param_samples[samp_num])}
-
-    @property
-    def extrema(self):
-        return np.asarray([dd.extrema for dd in self._parameters])
-
-    @property
-    def name(self):
-        return self.__class__.__name__
-
-    @property
-    def lib_shape(self):
-        return self.param_samples.shape
-
-    @property
-    def nsamples(self):
-        return self._nsamples
-
-    @property
-    def nparameters(self):
-        return self._nparameters
-
-    def model_for_sample_number(self, samp_num, sam_shape=None):
-        params = self.param_dict(samp_num)
-        self._log.debug(f"params {samp_num} :: {params}")
-        return self.model_for_params(params, sam_shape)
-
-    def normalized_params(self, vals):
-        """Params dict from normalized [0,1] values (``None`` -> parameter default) (``lib_tools.py:412-449``)."""
-        if np.ndim(vals) == 0:
-            vals = self.nparameters * [vals]
-        assert len(vals) == self.nparameters
-        assert np.all([(vv is None) or np.isfinite(vv) for vv in vals]), f"Not all `vals` are finite!  {vals}"
-        params = {}
-        for ii, pname in enumerate(self.param_names):
-            param = self._parameters[ii]
-            params[pname] = param.default if vals[ii] is None else param(vals[ii])
-        return params
-
-    def default_params(self):
-        return {param.name: param.default for param in self._parameters}
-
+# ==================================================================================================
+# Parameter distributions: maps of the unit interval onto parameter values (``lib_tools.py:467-712``)
+# ==================================================================================================
 
 class _Param_Dist(abc.ABC):
-    """Parameter distribution: maps [0, 1] to parameter values (``lib_tools.py:467-518``)."""
+    """A named one-dimensional distribution, evaluated through its quantile function on [0, 1]."""
 
     def __init__(self, name, default=None, clip=None):
-        if clip is not None:
-            assert len(clip) == 2
-        self._clip = clip
-        self._name = name
-        self._default = default
-
-    def __call__(self, xx):
-        rv = self._dist_func(xx)
-        if self._clip is not None:
-            rv = np.clip(rv, *self._clip)
-        return rv
+        if clip is not None and len(clip) != 2:
+            raise AssertionError("`clip` must be (lo, hi)")
+        self._name, self._default, self._clip = name, default, clip
 
     @abc.abstractmethod
-    def _dist_func(self, *args, **kwargs):
-        pass
+    def _dist_func(self, xx):
+        """quantile function"""
 
-    @property
-    def extrema(self):
-        return self(np.asarray([0.0, 1.0]))
+    def __call__(self, xx):
+        vals = self._dist_func(xx)
+        return vals if self._clip is None else np.clip(vals, *self._clip)
 
-    @property
-    def name(self):
-        return self._name
-
-    @property
-    def default(self):
-        if self._default is not None:
-            return self._default
-        return self(0.5)
+    name = property(lambda self: self._name)
+    extrema = property(lambda self: self(np.asarray([0.0, 1.0])))
+    default = property(lambda self: self(0.5) if self._default is None else self._default)
 
 
 class PD_Uniform(_Param_Dist):
-    """``lib_tools.py:520-531``"""
-
     def __init__(self, name, lo, hi, **kwargs):
         super().__init__(name, **kwargs)
-        self._lo = lo
-        self._hi = hi
+        self._lo, self._hi = lo, hi
 
     def _dist_func(self, xx):
         return self._lo + (self._hi - self._lo) * xx
 
 
 class PD_Uniform_Log(_Param_Dist):
-    """``lib_tools.py:533-545``"""
-
     def __init__(self, name, lo, hi, **kwargs):
         super().__init__(name, **kwargs)
         assert lo > 0.0 and hi > 0.0
-        self._lo_log10 = np.log10(lo)
-        self._hi_log10 = np.log10(hi)
+        self._lo_log10, self._hi_log10 = np.log10(lo), np.log10(hi)
 
     def _dist_func(self, xx):
         return np.power(10.0, self._lo_log10 + (self._hi_log10 - self._lo_log10) * xx)
 
 
 class PD_Normal(_Param_Dist):
-    """Normal distribution mapped from [0,1] through the ppf (``lib_tools.py:547-569``)."""
-
     def __init__(self, name, mean, stdev, clip=None, **kwargs):
         assert stdev > 0.0
         super().__init__(name, clip=clip, **kwargs)
-        self._mean = mean
-        self._stdev = stdev
+        self._mean, self._stdev = mean, stdev
         self._frozen_dist = sp.stats.norm(loc=mean, scale=stdev)
 
     def _dist_func(self, xx):
         return self._frozen_dist.ppf(xx)
+
+
+# ==================================================================================================
+# Parameter spaces (``lib_tools.py:34-465``)
+# ==================================================================================================
+
+class _Param_Space(abc.ABC):
+    """A library's parameter space: named distributions, their Latin-hypercube samples, and the recipe that turns
+    one sample into a ``(sam, hard)`` pair.  Same attributes / methods / file format as the reference's class;
+    subclasses give ``DEFAULTS`` and the two builders ``_init_sam(sam_shape, settings)``, ``_init_hard(sam, settings)``
+    (the concrete spaces of this package get them from ``librarian.recipes``)."""
+
+    __version__ = "0.0"
+    _SAVED_ATTRIBUTES = ["sam_shape", "param_names", "_uniform_samples", "param_samples", "_nsamples", "_nparameters"]
+    DEFAULTS = {}
+
+    def __init__(self, parameters, log=None, nsamples=None, sam_shape=None, seed=None, random_state=None):
+        log = holo.log if log is None else log
+        # the reference also seeds numpy's legacy global generator here (lib_tools.py:93-98)
+        if random_state is None:
+            np.random.seed(seed)
+            random_state = np.random.get_state()
+        else:
+            np.random.set_state(random_state)
+        if not (hasattr(parameters, "__len__") and len(parameters) > 0):
+            log.exception("`parameters` must be a list of `_Param_Dist` subclasses!")
+            raise TypeError("`parameters` must be a non-empty list of `_Param_Dist` objects")
+        for par in parameters:
+            if not isinstance(par, _Param_Dist):
+                err = f"{getattr(par, 'name', par)}: {par} is not a `_Param_Dist` object!"
+                log.exception(err)
+                raise ValueError(err)
+        self._log = log
+        self._parameters = parameters
+        self.param_names = [_canonical(par.name, log=log)[0] for par in parameters]
+        self._nparameters = len(parameters)
+        self._nsamples = nsamples
+        self._seed, self._random_state = seed, random_state
+        self.sam_shape = sam_shape
+        self._uniform_samples = self.param_samples = None
+        if nsamples is None:
+            log.info(f"{self}: {nsamples=} - cannot generate parameter samples.")
+        else:
+            # (S, D) points of a strength-1 Latin hypercube, pushed through each parameter's quantile function
+            self._uniform_samples = sp.stats.qmc.LatinHypercube(d=self._nparameters, strength=1, seed=seed).random(n=nsamples)
+            self.param_samples = np.column_stack([par(col) for par, col in zip(parameters, self._uniform_samples.T)])
+
+    # ---- models
+
+    def model_for_params(self, params, sam_shape=None):
+        """``(sam, hard)`` for a dict of parameter values on top of ``DEFAULTS`` (``lib_tools.py:156-212``)."""
+        settings = dict(self.DEFAULTS)
+        for name, value in params.items():
+            name, value = _canonical(name, value, log=self._log, convert=True)
+            settings[name] = value
+        sam = self._init_sam(self.sam_shape if sam_shape is None else sam_shape, settings)
+        return sam, self._init_hard(sam, settings)
+
+    def model_for_sample_number(self, samp_num, sam_shape=None):
+        return self.model_for_params(self.param_dict(samp_num), sam_shape)
+
+    @classmethod
+    @abc.abstractmethod
+    def _init_sam(cls, sam_shape, params):
+        raise NotImplementedError
+
+    @classmethod
+    @abc.abstractmethod
+    def _init_hard(cls, sam, params):
+        raise NotImplementedError
+
+    # ---- samples
+
+    def param_dict(self, samp_num):
+        return dict(zip(self.param_names, self.param_samples[samp_num]))
+
+    def default_params(self):
+        return {par.name: par.default for par in self._parameters}
+
+    def normalized_params(self, vals):
+        """Parameter dict from quantiles in [0, 1]; ``None`` entries take the parameter's default."""
+        if np.ndim(vals) == 0:
+            vals = [vals] * self.nparameters
+        assert len(vals) == self.nparameters
+        assert all((vv is None) or np.isfinite(vv) for vv in vals), f"Not all `vals` are finite!  {vals}"
+        return {name: (par.default if vv is None else par(vv)) for name, par, vv in zip(self.param_names, self._parameters, vals)}
+
+    extrema = property(lambda self: np.asarray([par.extrema for par in self._parameters]))
+    name = property(lambda self: type(self).__name__)
+    lib_shape = property(lambda self: self.param_samples.shape)
+    nsamples = property(lambda self: self._nsamples)
+    nparameters = property(lambda self: self._nparameters)
+
+    # ---- files (``<name>.pspace.npz``, the reference's keys)
+
+    def save(self, path_output):
+        path_output = Path(path_output)
+        if not path_output.is_dir():
+            err = f"save path {path_output} does not exist, or is not a directory!"
+            self._log.exception(err)
+            raise ValueError(err)
+        fname = path_output / f"{self.name}{PSPACE_FILE_SUFFIX}"
+        np.savez(fname, class_name=self.name, class_vers=self.__version__, librarian_version=holo.librarian.__version__,
+                 **{key: getattr(self, key) for key in self._SAVED_ATTRIBUTES})
+        return fname
+
+    @classmethod
+    def from_save(cls, fname, log=None):
+        log = holo.log if log is None else log
+        data = np.load(fname, allow_pickle=True)
+        space_class = holo.librarian.param_spaces_dict.get(str(data['class_name'][()]))
+        if space_class is None:
+            log.warning(f"pspace file {fname} has class_name={data['class_name'][()]!r}, not in `param_spaces_dict`!")
+            space_class = cls
+        samples = data['param_samples'][()]
+        nsamples = None if samples is None else samples.shape[0]
+        space = space_class(nsamples=nsamples, log=log)
+        if list(data['param_names']) != list(space.param_names):
+            err = f"Mismatch between loaded parameter names ({data['param_names']}) and class parameter names ({space.param_names})!"
+            log.exception(err)
+            raise RuntimeError(err)
+        fallback = {'_nsamples': nsamples, '_nparameters': None if samples is None else samples.shape[1]}
+        for key in space._SAVED_ATTRIBUTES:
+            setattr(space, key, data[key][()] if key in data.files else fallback[key])
+        return space
 
 
 def run_model(

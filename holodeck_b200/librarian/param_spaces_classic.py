@@ -1,202 +1,51 @@
-"""'Classic' parameter spaces used in the NANOGrav 15yr analysis (``librarian/param_spaces_classic.py``)."""
-from holodeck_b200.constants import PC, GYR
-from holodeck_b200.librarian.lib_tools import _Param_Space, PD_Uniform, PD_Normal
-from holodeck_b200 import sams, hardening, host_relations
+"""The 'classic' parameter spaces of the NANOGrav 15 yr analysis (``librarian/param_spaces_classic.py``), declared as
+data for ``librarian.recipes``: model components, default settings (``:13-42, 150-176``) and sampled distributions
+(``:92-145, 235-253``).  Class names, parameter names, defaults and distributions are the reference's."""
+from holodeck_b200.librarian.recipes import define_space, PD_Uniform as U, PD_Normal as N
 
+# default settings shared by the phenomenological spaces: 2-power-law hardening [Gyr, pc], GSMF fit to [Tomczak+2014]
+# (`sam-parameters.ipynb`), pair fraction, merger time [Gyr] (qgamma: Boylan-Kolchin+2008), M-Mbulge (mean of MM2013 and
+# KH2013) with its 0.3 dex scatter
+_GALAXY = dict(
+    gsmf_phiz=-0.6, gsmf_mchar0_log10=11.24, gsmf_mcharz=0.11, gsmf_alpha0=-1.21, gsmf_alphaz=-0.03,
+    gpf_frac_norm_allq=0.025, gpf_malpha=0.0, gpf_qgamma=0.0, gpf_zbeta=1.0, gpf_max_frac=1.0,
+    gmt_norm=0.5, gmt_malpha=0.0, gmt_qgamma=-1.0, gmt_zbeta=-0.5,
+    mmb_mamp_log10=8.69, mmb_plaw=1.10, mmb_scatter_dex=0.3,
+)
+_PHENOM = dict(hard_time=3.0, hard_sepa_init=1e4, hard_rchar=100.0, hard_gamma_inner=-1.0, hard_gamma_outer=+2.5,
+               gsmf_phi0_log10=-2.77, **_GALAXY)
+_PHENOM_MODEL = dict(sam=dict(gsmf="gsmf_schechter", gpf="gpf_power_law", gmt="gmt_power_law", mmbulge="mmbulge_kh2013"),
+                     hard="hard_fixed_time_2pl")
 
-class _PS_Classic_Phenom(_Param_Space):
-    """Base class for the classic phenomenological parameter spaces (``param_spaces_classic.py:10-89``)."""
+_PS_Classic_Phenom = define_space(
+    "_PS_Classic_Phenom", "Base of the classic phenomenological spaces (no sampled parameters).", _PHENOM, lambda: [], **_PHENOM_MODEL)
 
-    DEFAULTS = dict(
-        hard_time=3.0,          # [Gyr]
-        hard_sepa_init=1e4,     # [pc]
-        hard_rchar=100.0,       # [pc]
-        hard_gamma_inner=-1.0,
-        hard_gamma_outer=+2.5,
+PS_Classic_Phenom_Uniform = define_space(
+    "PS_Classic_Phenom_Uniform", "Classic 6D phenomenological, uniform parameter space ('phenom-uniform').", _PHENOM,
+    lambda: [U("gsmf_phi0_log10", -3.5, -1.5), U("gsmf_mchar0_log10", 10.5, 12.5), U("mmb_mamp_log10", +7.6, +9.0),
+             U("mmb_scatter_dex", +0.0, +0.9), U("hard_time", 0.1, 11.0), U("hard_gamma_inner", -1.5, +0.0)],
+    base=_PS_Classic_Phenom, **_PHENOM_MODEL)
 
-        # Parameters are based on `sam-parameters.ipynb` fit to [Tomczak+2014]
-        gsmf_phi0_log10=-2.77,
-        gsmf_phiz=-0.6,
-        gsmf_mchar0_log10=11.24,
-        gsmf_mcharz=0.11,
-        gsmf_alpha0=-1.21,
-        gsmf_alphaz=-0.03,
+PS_Classic_Phenom_Astro_Extended = define_space(
+    "PS_Classic_Phenom_Astro_Extended", "Classic 12D phenomenological parameter space ('phenom-astro+extended'): "
+    "normal priors from `sam-parameters.ipynb` fits to [Tomczak+2014] with 4x standard deviations.", _PHENOM,
+    lambda: [U("hard_time", 0.1, 11.0), U("hard_gamma_inner", -1.5, +0.5),
+             N("gsmf_phi0", -2.56, 0.4), N("gsmf_mchar0_log10", 10.9, 0.4), N("gsmf_alpha0", -1.2, 0.2),
+             N("gpf_zbeta", +0.8, 0.4), N("gpf_qgamma", +0.5, 0.3),
+             U("gmt_norm", 0.2, 5.0), U("gmt_zbeta", -2.0, +0.0),
+             N("mmb_mamp_log10", +8.6, 0.2), N("mmb_plaw", +1.2, 0.2), N("mmb_scatter_dex", +0.32, 0.15)],
+    base=_PS_Classic_Phenom, **_PHENOM_MODEL)
 
-        gpf_frac_norm_allq=0.025,
-        gpf_malpha=0.0,
-        gpf_qgamma=0.0,
-        gpf_zbeta=1.0,
-        gpf_max_frac=1.0,
+# GW-only evolution.  Kept from the reference (`:148-253`): the defaults and the model read `gsmf_phi0`, while a sampled
+# parameter of that name is renamed to `gsmf_phi0_log10` (lib_tools.PARAM_NAMES_REPLACE), and the sampled `mmb_scatter`
+# is not the `mmb_scatter_dex` the model reads -- those two samples do not reach the model.
+_GWONLY_MODEL = dict(sam=dict(gsmf="gsmf_schechter_phi0", gpf="gpf_power_law", gmt="gmt_power_law", mmbulge="mmbulge_kh2013"),
+                     hard="hard_gw")
+_PS_Classic_GWOnly = define_space(
+    "_PS_Classic_GWOnly", "Base of the classic GW-only spaces.", dict(gsmf_phi0=-2.77, **_GALAXY), lambda: [], **_GWONLY_MODEL)
 
-        gmt_norm=0.5,           # [Gyr]
-        gmt_malpha=0.0,
-        gmt_qgamma=-1.0,        # Boylan-Kolchin+2008
-        gmt_zbeta=-0.5,
-
-        mmb_mamp_log10=8.69,
-        mmb_plaw=1.10,          # average MM2013 and KH2013
-        mmb_scatter_dex=0.3,
-    )
-
-    @classmethod
-    def _init_sam(cls, sam_shape, params):
-        gsmf = sams.GSMF_Schechter(
-            phi0=params['gsmf_phi0_log10'],
-            phiz=params['gsmf_phiz'],
-            mchar0_log10=params['gsmf_mchar0_log10'],
-            mcharz=params['gsmf_mcharz'],
-            alpha0=params['gsmf_alpha0'],
-            alphaz=params['gsmf_alphaz'],
-        )
-        gpf = sams.GPF_Power_Law(
-            frac_norm_allq=params['gpf_frac_norm_allq'],
-            malpha=params['gpf_malpha'],
-            qgamma=params['gpf_qgamma'],
-            zbeta=params['gpf_zbeta'],
-            max_frac=params['gpf_max_frac'],
-        )
-        gmt = sams.GMT_Power_Law(
-            time_norm=params['gmt_norm']*GYR,
-            malpha=params['gmt_malpha'],
-            qgamma=params['gmt_qgamma'],
-            zbeta=params['gmt_zbeta'],
-        )
-        mmbulge = host_relations.MMBulge_KH2013(
-            mamp_log10=params['mmb_mamp_log10'],
-            mplaw=params['mmb_plaw'],
-            scatter_dex=params['mmb_scatter_dex'],
-        )
-        return sams.Semi_Analytic_Model(gsmf=gsmf, gpf=gpf, gmt=gmt, mmbulge=mmbulge, shape=sam_shape)
-
-    @classmethod
-    def _init_hard(cls, sam, params):
-        return hardening.Fixed_Time_2PL_SAM(
-            sam,
-            params['hard_time']*GYR,
-            sepa_init=params['hard_sepa_init']*PC,
-            rchar=params['hard_rchar']*PC,
-            gamma_inner=params['hard_gamma_inner'],
-            gamma_outer=params['hard_gamma_outer'],
-        )
-
-
-class PS_Classic_Phenom_Uniform(_PS_Classic_Phenom):
-    """Classic 6D phenomenological, uniform parameter space ('phenom-uniform') (``:92-111``)."""
-
-    def __init__(self, log=None, nsamples=None, sam_shape=None, seed=None):
-        parameters = [
-            PD_Uniform("gsmf_phi0_log10", -3.5, -1.5),
-            PD_Uniform("gsmf_mchar0_log10", 10.5, 12.5),   # [log10(Msol)]
-            PD_Uniform("mmb_mamp_log10", +7.6, +9.0),      # [log10(Msol)]
-            PD_Uniform("mmb_scatter_dex", +0.0, +0.9),
-            PD_Uniform("hard_time", 0.1, 11.0),            # [Gyr]
-            PD_Uniform("hard_gamma_inner", -1.5, +0.0),
-        ]
-        super().__init__(parameters, log=log, nsamples=nsamples, sam_shape=sam_shape, seed=seed)
-
-
-class PS_Classic_Phenom_Astro_Extended(_PS_Classic_Phenom):
-    """Classic 12D phenomenological parameter space ('phenom-astro+extended') (``:114-145``)."""
-
-    def __init__(self, log=None, nsamples=None, sam_shape=None, seed=None):
-        parameters = [
-            PD_Uniform("hard_time", 0.1, 11.0),   # [Gyr]
-            PD_Uniform("hard_gamma_inner", -1.5, +0.5),
-
-            # from `sam-parameters.ipynb` fits to [Tomczak+2014] with 4x stdev values
-            PD_Normal("gsmf_phi0", -2.56, 0.4),
-            PD_Normal("gsmf_mchar0_log10", 10.9, 0.4),   # [log10(Msol)]
-            PD_Normal("gsmf_alpha0", -1.2, 0.2),
-
-            PD_Normal("gpf_zbeta", +0.8, 0.4),
-            PD_Normal("gpf_qgamma", +0.5, 0.3),
-
-            PD_Uniform("gmt_norm", 0.2, 5.0),    # [Gyr]
-            PD_Uniform("gmt_zbeta", -2.0, +0.0),
-
-            PD_Normal("mmb_mamp_log10", +8.6, 0.2),   # [log10(Msol)]
-            PD_Normal("mmb_plaw", +1.2, 0.2),
-            PD_Normal("mmb_scatter_dex", +0.32, 0.15),
-        ]
-        super().__init__(parameters, log=log, nsamples=nsamples, sam_shape=sam_shape, seed=seed)
-
-
-class _PS_Classic_GWOnly(_Param_Space):
-    """Base class for the classic GW-only parameter spaces (``param_spaces_classic.py:148-232``).
-
-    NOTE (kept from the reference): ``DEFAULTS`` and ``_init_sam`` use the key ``gsmf_phi0`` while the
-    sampled parameter of that name is renamed to ``gsmf_phi0_log10`` by ``PARAM_NAMES_REPLACE``, and the
-    sampled ``mmb_scatter`` is not read (``mmb_scatter_dex`` is), so those two samples do not reach the
-    model.
-    """
-
-    DEFAULTS = dict(
-        gsmf_phi0=-2.77,
-        gsmf_phiz=-0.6,
-        gsmf_mchar0_log10=11.24,
-        gsmf_mcharz=0.11,
-        gsmf_alpha0=-1.21,
-        gsmf_alphaz=-0.03,
-
-        gpf_frac_norm_allq=0.025,
-        gpf_malpha=0.0,
-        gpf_qgamma=0.0,
-        gpf_zbeta=1.0,
-        gpf_max_frac=1.0,
-
-        gmt_norm=0.5,           # [Gyr]
-        gmt_malpha=0.0,
-        gmt_qgamma=-1.0,
-        gmt_zbeta=-0.5,
-
-        mmb_mamp_log10=8.69,
-        mmb_plaw=1.10,
-        mmb_scatter_dex=0.3,
-    )
-
-    @classmethod
-    def _init_sam(cls, sam_shape, params):
-        gsmf = sams.GSMF_Schechter(
-            phi0=params['gsmf_phi0'],
-            phiz=params['gsmf_phiz'],
-            mchar0_log10=params['gsmf_mchar0_log10'],
-            mcharz=params['gsmf_mcharz'],
-            alpha0=params['gsmf_alpha0'],
-            alphaz=params['gsmf_alphaz'],
-        )
-        gpf = sams.GPF_Power_Law(
-            frac_norm_allq=params['gpf_frac_norm_allq'],
-            malpha=params['gpf_malpha'],
-            qgamma=params['gpf_qgamma'],
-            zbeta=params['gpf_zbeta'],
-            max_frac=params['gpf_max_frac'],
-        )
-        gmt = sams.GMT_Power_Law(
-            time_norm=params['gmt_norm']*GYR,
-            malpha=params['gmt_malpha'],
-            qgamma=params['gmt_qgamma'],
-            zbeta=params['gmt_zbeta'],
-        )
-        mmbulge = host_relations.MMBulge_KH2013(
-            mamp_log10=params['mmb_mamp_log10'],
-            mplaw=params['mmb_plaw'],
-            scatter_dex=params['mmb_scatter_dex'],
-        )
-        return sams.Semi_Analytic_Model(gsmf=gsmf, gpf=gpf, gmt=gmt, mmbulge=mmbulge, shape=sam_shape)
-
-    @classmethod
-    def _init_hard(cls, sam, params):
-        return hardening.Hard_GW()
-
-
-class PS_Classic_GWOnly_Uniform(_PS_Classic_GWOnly):
-    """Classic 4D GW-only, uniform parameter space ('gw-only') (``:235-253``)."""
-
-    def __init__(self, log=None, nsamples=None, sam_shape=None, seed=None):
-        parameters = [
-            PD_Uniform("gsmf_phi0", -3.5, -1.5),
-            PD_Uniform("gsmf_mchar0_log10", 10.5, 12.5),   # [log10(Msol)]
-            PD_Uniform("mmb_mamp_log10", +7.5, +9.5),      # [log10(Msol)]
-            PD_Uniform("mmb_scatter", +0.0, +1.2),
-        ]
-        _Param_Space.__init__(self, parameters, log=log, nsamples=nsamples, sam_shape=sam_shape, seed=seed)
+PS_Classic_GWOnly_Uniform = define_space(
+    "PS_Classic_GWOnly_Uniform", "Classic 4D GW-only, uniform parameter space ('gw-only').", dict(gsmf_phi0=-2.77, **_GALAXY),
+    lambda: [U("gsmf_phi0", -3.5, -1.5), U("gsmf_mchar0_log10", 10.5, 12.5), U("mmb_mamp_log10", +7.5, +9.5),
+             U("mmb_scatter", +0.0, +1.2)],
+    base=_PS_Classic_GWOnly, **_GWONLY_MODEL)

@@ -6,11 +6,10 @@ set -u
 OUT=gpurun_out/r2_multigpu
 mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-for N in 8 2; do
-  $TR --nproc-per-node $N --master-port 2950$N bench.py --gpus $N --steps 10 --warmup 3 > $OUT/bench_weak_n$N.json 2> $OUT/bench_weak_n$N.err
+# (the driver records the weak-scaling curve itself at round end: SCALE_r02.json; here the STRONG-scaling line)
+for N in ${HOLO_STRONG_NS:-8}; do
   $TR --nproc-per-node $N --master-port 2951$N bench.py --gpus $N --steps 10 --warmup 3 --scaling strong --no-cpu-baseline > $OUT/bench_strong_n$N.json 2> $OUT/bench_strong_n$N.err
 done
-python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_n1.json 2> $OUT/bench_n1.err
 GL="-m holodeck_b200.librarian.gen_lib PS_Classic_Phenom_Uniform"
 rm -rf /tmp/lib1 /tmp/lib8 /tmp/lib8w1 /tmp/lib1ref
 python $GL /tmp/lib1ref -n 60 -r 100 -l 5 --gwb --ss --params --seed 1 --no-streaming > $OUT/genlib_1gpu_reference_fileplane.log 2>&1
