@@ -50,8 +50,8 @@ class SamParams(C.Structure):
         ("gsmf_uses_mtot", C.c_int),
         ("gpf_uses_mtot", C.c_int),
         ("gmt_uses_mtot", C.c_int),
-        ("_pad0", C.c_int),
-        ("_pad1", C.c_int),
+        ("bf_kind", C.c_int),
+        ("bf_n", C.c_int),
         ("gsmf", C.c_double * 12),
         ("gpf", C.c_double * 6),
         ("gmt", C.c_double * 5),
@@ -60,6 +60,7 @@ class SamParams(C.Structure):
         ("hubble_time", C.c_double),
         ("om0", C.c_double),
         ("age_universe", C.c_double),
+        ("bf", C.c_double * 4),
     ]
 
 
@@ -96,6 +97,7 @@ class LoudestArgs(C.Structure):
         ("gwb_R", C.c_int),
         ("gwb_r0", C.c_int64),
         ("gwb_seed", C.c_uint64),
+        ("defer_check", C.c_int),
     ]
 
 
@@ -191,7 +193,7 @@ SIGNATURES = {
     "holo_launch_count": [],
     "holo_set_profiling": [_I],
     "holo_get_profile": [_P, _I],
-    "holo_sam_density": [_P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(SamParams), _P, _P, _P, _P],
+    "holo_sam_density": [_P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(SamParams), _P, _P, _P, _P, _P],
     "holo_zero_stalled": [_P, _P, _L, _P],
     "holo_find_2pwl_hardening_norm": [CyConsts, _D, _P, _P, _I, _D, _D, _D, _D, _I, _P, _P],
     "holo_binary_lifetime_2pwl": [CyConsts, _P, _P, _P, _I, _D, _D, _D, _D, _I, _P, _P],

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256)
 density_kernel(const double* __restrict__ mtot, const double* __restrict__ mrat,
                const double* __restrict__ redz, const double* __restrict__ age_z,
                const double* __restrict__ dtdz_z, int M, int Q, int Z, holo_sam_params par,
-               double* __restrict__ dens, double* __restrict__ gmt_time,
+               const double* __restrict__ bf_tab, double* __restrict__ dens, double* __restrict__ gmt_time,
                double* __restrict__ redz_prime) {
     int64_t n = (int64_t)M * Q * Z;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
@@ -34,7 +34,7 @@ density_kernel(const double* __restrict__ mtot, const double* __restrict__ mrat,
         int64_t mq = i / Z;
         int jj = (int)(mq % Q);
         int ii = (int)(mq / Q);
-        DensityOut o = density_point(par, mtot[ii], mrat[jj], redz[kk], age_z[kk], dtdz_z[kk]);
+        DensityOut o = density_point(par, bf_tab, mtot[ii], mrat[jj], redz[kk], age_z[kk], dtdz_z[kk]);
         dens[i] = o.dens;
         if (gmt_time) gmt_time[i] = o.gmt_time;
         if (redz_prime) redz_prime[i] = o.redz_prime;
@@ -473,14 +473,17 @@ using namespace holo;
 extern "C" {
 
 int holo_sam_density(const double* mtot, const double* mrat, const double* redz, const double* age_z,
-                     const double* dtdz_z, int M, int Q, int Z, const holo_sam_params* par,
+                     const double* dtdz_z, int M, int Q, int Z, const holo_sam_params* par, const double* bf_tables,
                      double* dens, double* gmt_time, double* redz_prime, void* stream) {
     HOLO_REQUIRE(mtot && mrat && redz && age_z && dtdz_z && par && dens, "holo_sam_density: NULL argument");
     HOLO_REQUIRE(M > 0 && Q > 0 && Z > 0, "holo_sam_density: bad shape");
-    HOLO_REQUIRE(par->mmb[3] > 0.0, "holo_sam_density: bulge fraction must be > 0");
+    HOLO_REQUIRE(par->bf_kind == 0 || par->bf_kind == 1, "holo_sam_density: unknown bulge-fraction kind");
+    if (par->bf_kind == 0) HOLO_REQUIRE(par->mmb[3] > 0.0, "holo_sam_density: bulge fraction must be > 0");
+    else HOLO_REQUIRE(bf_tables && par->bf_n > 0 && par->bf[0] > 0.0 && par->bf[1] >= par->bf[0] && par->bf[2] > 0.0,
+                      "holo_sam_density: BF_Sigmoid needs its spline tables and parameters");
     int64_t n = (int64_t)M * Q * Z;
     density_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        mtot, mrat, redz, age_z, dtdz_z, M, Q, Z, *par, dens, gmt_time, redz_prime); holo::count_launches(1);
+        mtot, mrat, redz, age_z, dtdz_z, M, Q, Z, *par, bf_tables, dens, gmt_time, redz_prime); holo::count_launches(1);
     return holo_check_launch("holo_sam_density");
 }
 

@@ -12,19 +12,49 @@ namespace holo {
 // K0: static binary density   (reference: holodeck/sams/sam.py:250-365)
 // =================================================================================================
 
+// BF_Sigmoid (host_relations.py:198-331): its inverse relations are scipy quadratic interpolants; the host hands
+// them over as piecewise polynomials [breaks (n+1) | c0 (n) | c1 (n) | c2 (n)] (first / last piece extrapolate).
+HOLO_HD double bf_spline(const double* tab, int n, double x) {
+    int lo = 0, hi = n;                       // largest lo in [0, n-1] with breaks[lo] <= x (clamped)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tab[mid] <= x) lo = mid; else hi = mid;
+    }
+    const double dx = x - tab[lo];
+    const double* c = tab + (n + 1);
+    return (c[lo] * dx + c[n + lo]) * dx + c[2 * n + lo];
+}
+
+// BF_Sigmoid.bulge_frac host_relations.py:286-295
+HOLO_HD double bf_sigmoid_frac(const holo_sam_params& p, double mstar) {
+    double mm = mstar / p.bf[2];
+    if (mm > 1.0) mm = 1.0;
+    const double frac = p.bf[0] + (p.bf[1] - p.bf[0]) / (1.0 + pow((1.0 / mm) - 1.0, p.bf[3]));
+    return ((mm >= 1.0) || (frac > p.bf[1])) ? p.bf[1] : frac;
+}
+
 // MMBulge_Standard.mstar_from_mbh: host_relations.py:768-771 -> mbulge_from_mbh :745-765 ->
-// _log10_relation_reverse :1137-1178 ; BF_Constant.mstar_from_mbulge :190-192
-HOLO_HD double mstar_from_mbh(const holo_sam_params& p, double mbh) {
+// _log10_relation_reverse :1137-1178 ; BF_Constant.mstar_from_mbulge :190-192 / BF_Sigmoid.mstar_from_mbulge :297-308
+HOLO_HD double mstar_from_mbh(const holo_sam_params& p, const double* bf_tab, double mbh) {
     double xx = log10(mbh / p.mmb[0]);
     xx = 1.0 / p.mmb[1] * xx;
     double mbulge = p.mmb[2] * pow(10.0, xx);
-    return mbulge / p.mmb[3];
+    if (p.bf_kind == 0) return mbulge / p.mmb[3];
+    const double mstar = mbulge / p.bf[1];
+    return ((mstar / p.bf[2]) < 1.0) ? bf_spline(bf_tab, p.bf_n, mbulge) : mstar;
 }
 
 // _MMBulge_Relation.dmstar_dmbh host_relations.py:483-512 with MMBulge_Standard.dmbulge_dmbh :720-743
-HOLO_HD double dmstar_dmbh(const holo_sam_params& p, double mstar) {
-    double mbulge = mstar * p.mmb[3];
-    double dmstar_dmbulge = 1.0 / p.mmb[3];
+HOLO_HD double dmstar_dmbh(const holo_sam_params& p, const double* bf_tab, double mstar) {
+    double mbulge, dmstar_dmbulge;
+    if (p.bf_kind == 0) {
+        mbulge = mstar * p.mmb[3];
+        dmstar_dmbulge = 1.0 / p.mmb[3];
+    } else {
+        mbulge = mstar * bf_sigmoid_frac(p, mstar);                    // _Bulge_Frac.mbulge_from_mstar :113-131
+        // BF_Sigmoid.dmstar_dmbulge :310-321 (second table)
+        dmstar_dmbulge = ((mbulge / p.bf[2]) < p.bf[1]) ? bf_spline(bf_tab + 4 * p.bf_n + 1, p.bf_n, mbulge) : 1.0 / p.bf[1];
+    }
     // mbh_from_mbulge -> _log10_relation (host_relations.py:1102-1134)
     double yy = log10(mbulge / p.mmb[2]) * p.mmb[1];
     double mbh = p.mmb[0] * pow(10.0, yy);
@@ -82,14 +112,14 @@ struct DensityOut {
 };
 
 // One (M,q,z) grid point of sam.py:310-365.
-HOLO_HD DensityOut density_point(const holo_sam_params& p, double mtot, double mrat, double redz,
+HOLO_HD DensityOut density_point(const holo_sam_params& p, const double* bf_tab, double mtot, double mrat, double redz,
                                  double age_z, double dtdz_z) {
     DensityOut out;
     // mass_stellar(): sam.py:250-278 ; utils.m1m2_from_mtmr utils.py:1620-1642
     double m1 = mtot / (1.0 + mrat);
     double m2 = mtot - m1;
-    double mstar_pri = mstar_from_mbh(p, m1);
-    double mstar_sec = mstar_from_mbh(p, m2);
+    double mstar_pri = mstar_from_mbh(p, bf_tab, m1);
+    double mstar_sec = mstar_from_mbh(p, bf_tab, m2);
     double mstar_rat = mstar_sec / mstar_pri;
     double mstar_tot = mstar_pri + mstar_sec;
     double mass_gsmf = p.gsmf_uses_mtot ? mstar_tot : mstar_pri;
@@ -121,7 +151,7 @@ HOLO_HD DensityOut density_point(const holo_sam_params& p, double mtot, double m
     double dens = gsmf_eval(p, mass_gsmf, redz) * rate * dtdz_z;    // sam.py:347
     double mplaw = p.mmb[1];
     double dqbh_dqgal = mplaw * pow(mstar_rat, mplaw - 1.0);         // sam.py:355
-    double dmstar_dmbh_pri = dmstar_dmbh(p, mstar_pri);              // sam.py:357
+    double dmstar_dmbh_pri = dmstar_dmbh(p, bf_tab, mstar_pri);      // sam.py:357
     double qterm = (1.0 + mstar_rat) / (1.0 + mrat);                 // sam.py:358
     double dms = dmstar_dmbh_pri * qterm;
     dens *= (mtot / mstar_tot) * (dms / dqbh_dqgal);                 // sam.py:365

@@ -120,7 +120,7 @@ def sam_poisson_gwb(dist, hc2, nreals, normal_threshold=1e10, *, seed=None, coun
 
 def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold,
              mt=None, mr=None, rz=None, redz_final=None, dcom_final=None, sepa=None, angs=None,
-             seed=None, counts=None, r0=0, gwb_nreals=None, gwb_seed=None, gwb_r0=0, order=None):
+             seed=None, counts=None, r0=0, gwb_nreals=None, gwb_seed=None, gwb_r0=0, order=None, defer=None):
     import torch
     lib = _lib.require_gpu()
     number = _lib.to_dev(number)
@@ -179,6 +179,22 @@ def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, norm
         args.gwb = out["gwb"].data_ptr()
         args.gwb_R, args.gwb_r0, args.gwb_seed = Rg, int(gwb_r0), _seed(gwb_seed)
 
+    if defer is not None:
+        # One attempt with the library's default head / bucket, the overflow flags left on the device: `defer` (a list)
+        # receives an int32 view of them; the caller checks it at its next synchronisation point and repeats the call
+        # without `defer` if either is set (never observed at the named configurations).
+        args.bucket_cap, args.head_margin, args.defer_check = 0, 0.0, 1
+        nbytes = lib.holo_loudest_workspace_bytes(variant, ncell, F, R, L, 0)
+        if Rg > 0:
+            nbytes += lib.holo_realize_workspace_bytes(0, ncell, F, Rg)
+        ws = _workspace(nbytes)
+        args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+        rc = lib.holo_loudest(C.byref(args), _lib.stream())
+        STATS["loudest_calls"] += 1
+        _lib.check(rc, "loudest")
+        defer.append(ws[:8].view(torch.int32))
+        return out
+
     cap, margin = 0, 0.0
     for attempt in range(_MAX_RETRY):
         args.bucket_cap = cap
@@ -204,7 +220,7 @@ def _loudest(variant, number, h2fdf, nreals, nloudest, msort, qsort, zsort, norm
 
 def loudest_hc_from_sorted(number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold=1e10, *,
                            seed=None, counts=None, r0=0, device=False, gwb_nreals=None, gwb_seed=None, gwb_r0=0,
-                           order=None):
+                           order=None, _defer=None):
     """Characteristic strain of the `nloudest` loudest single sources and of the background of all
     other sources (cyutils.pyx:1220-1344).
 
@@ -217,7 +233,8 @@ def loudest_hc_from_sorted(number, h2fdf, nreals, nloudest, msort, qsort, zsort,
     ``gwb_seed``), appended to the result as ``gwb`` (F, gwb_nreals).
     """
     out = _loudest(1, number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold,
-                   seed=seed, counts=counts, r0=r0, gwb_nreals=gwb_nreals, gwb_seed=gwb_seed, gwb_r0=gwb_r0, order=order)
+                   seed=seed, counts=counts, r0=r0, gwb_nreals=gwb_nreals, gwb_seed=gwb_seed, gwb_r0=gwb_r0, order=order,
+                   defer=_defer)
     res = (_out(out["hc2ss"], device), _out(out["hc2bg"], device))
     return res + ((_out(out["gwb"], device),) if "gwb" in out else ())
 
@@ -238,7 +255,7 @@ def loudest_hc_and_par_from_sorted(number, h2fdf, nreals, nloudest, mt, mr, rz, 
 def loudest_hc_and_par_from_sorted_redz(number, h2fdf, nreals, nloudest, mt, mr, rz, redz_final, dcom_final,
                                         sepa, angs, msort, qsort, zsort, normal_threshold=1e10, *,
                                         seed=None, counts=None, r0=0, device=False, gwb_nreals=None, gwb_seed=None,
-                                        gwb_r0=0, order=None):
+                                        gwb_r0=0, order=None, _defer=None):
     """As :func:`loudest_hc_from_sorted` for self-consistent hardening: per-source parameters
     ``sspar`` = (M, q, z_initial, z_final) and hc^2-weighted background means ``bgpar`` =
     (M, q, z_initial, z_final, d_c, a, theta) (cyutils.pyx:1541-1767).  Bins with ``h2fdf == 0`` are
@@ -249,7 +266,8 @@ def loudest_hc_and_par_from_sorted_redz(number, h2fdf, nreals, nloudest, mt, mr,
     """
     out = _loudest(3, number, h2fdf, nreals, nloudest, msort, qsort, zsort, normal_threshold,
                    mt=mt, mr=mr, rz=rz, redz_final=redz_final, dcom_final=dcom_final, sepa=sepa, angs=angs,
-                   seed=seed, counts=counts, r0=r0, gwb_nreals=gwb_nreals, gwb_seed=gwb_seed, gwb_r0=gwb_r0, order=order)
+                   seed=seed, counts=counts, r0=r0, gwb_nreals=gwb_nreals, gwb_seed=gwb_seed, gwb_r0=gwb_r0, order=order,
+                   defer=_defer)
     return tuple(_out(out[kk], device) for kk in ("hc2ss", "hc2bg", "sspar", "bgpar") + (("gwb",) if "gwb" in out else ()))
 
 

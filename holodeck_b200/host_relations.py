@@ -1,12 +1,14 @@
 """MBH--host scaling relations on the SAM path (subset of ``holodeck/host_relations.py``).
 
 In scope: the power-law M-Mbulge relations ``MMBulge_Standard`` /
-``MMBulge_KH2013`` / ``MMBulge_MM2013`` with a constant bulge fraction ``BF_Constant``.  These are the
-closed forms that the density kernel (K0, ``csrc/holo_math.cuh``) evaluates on the device; the numpy
-methods here are the same public callables the reference exposes, for host-side use.
+``MMBulge_KH2013`` / ``MMBulge_MM2013`` with a constant bulge fraction ``BF_Constant`` or the sigmoid
+``BF_Sigmoid`` (used by the ``PS_Astro_Strong_*`` parameter spaces).  The density kernel (K0,
+``csrc/holo_math.cuh``) evaluates them on the device -- closed forms, plus, for the sigmoid's numerically
+inverted relations, the same quadratic splines scipy builds here, handed over as piecewise polynomials;
+the numpy methods are the public callables the reference exposes, for host-side use.
 
-Out of scope: ``BF_Sigmoid`` (interp1d inverse), ``MMBulge_Redshift*``, M-sigma and stellar-mass
-halo-mass relations -- not reachable from the named configurations.
+Out of scope: ``MMBulge_Redshift*``, M-sigma and stellar-mass halo-mass relations -- not reachable from
+the named configurations.
 """
 import abc
 
@@ -50,6 +52,78 @@ class BF_Constant(_Bulge_Frac):
 
     def dmstar_dmbulge(self, mbulge, redz=None, **kwargs):
         return 1.0 / self.bulge_frac()
+
+
+class BF_Sigmoid(_Bulge_Frac):
+    r"""Stellar-bulge mass fraction rising from ``bulge_frac_lo`` to ``bulge_frac_hi`` with stellar mass
+    (``host_relations.py:198-331``):
+
+    .. math:: f_b(m < m_c) = f_l + (f_h - f_l) / [1 + ((m / m_c)^{-1} - 1)^k],  \qquad  f_b(m \ge m_c) = f_h.
+
+    The inverse relations (stellar mass and its derivative as functions of BULGE mass) have no closed form; like
+    the reference they are quadratic ``scipy.interpolate.interp1d`` interpolants over a 210-point grid that is
+    dense around the transition.  ``_kernel_tables`` exports the two splines as piecewise polynomials for K0.
+    """
+
+    _INTERP_GRID_SIZE = 200
+    _DERIV_DELTA = 1.0e-6
+
+    def __init__(self, bulge_frac_lo=0.5, bulge_frac_hi=1.0, mstar_char_log10=11.0, width_dex=1.0):
+        import scipy.interpolate
+        assert (0.0 < bulge_frac_lo) and (bulge_frac_lo <= 1.0), f"{bulge_frac_lo=} must be in (0.0, 1.0]!"
+        assert (0.0 < bulge_frac_hi) and (bulge_frac_hi <= 1.0), f"{bulge_frac_hi=} must be in (0.0, 1.0]!"
+        assert (bulge_frac_lo < bulge_frac_hi), f"{bulge_frac_lo=} must be less than {bulge_frac_hi=} !"
+        assert not (width_dex < 0.0), f"{width_dex=} must be non-negative!"
+        self._bulge_frac_lo, self._bulge_frac_hi = bulge_frac_lo, bulge_frac_hi
+        self._mstar_char = (10.0 ** mstar_char_log10) * MSOL
+        self._width_dex = width_dex
+        # stellar-mass grid: half of the points in [x_c - w/2, x_c + 1/2] dex, half over the ten decades below,
+        # ten more over the ten decades above (host_relations.py:251-263)
+        xc = np.log10(self._mstar_char)
+        lo, hi = xc - 0.5 * width_dex, xc + 0.5
+        half = self._INTERP_GRID_SIZE // 2
+        ms = np.concatenate([np.logspace(lo - 10.0, lo, half, endpoint=False), np.logspace(lo, hi, half, endpoint=False),
+                             np.logspace(hi, hi + 10.0, 10)])
+        mb = self.mbulge_from_mstar(ms)
+        dd = self._DERIV_DELTA
+        ms_lo, ms_hi = ms * (1.0 - dd / 2.0), ms * (1.0 + dd / 2.0)
+        dms_dmb = (ms_hi - ms_lo) / (self.mbulge_from_mstar(ms_hi) - self.mbulge_from_mstar(ms_lo))     # central difference
+        self._interp_mstar_from_mbulge = scipy.interpolate.interp1d(mb, ms, kind='quadratic', fill_value='extrapolate')
+        self._interp_dmstar_dmbulge_from_mbulge = scipy.interpolate.interp1d(mb, dms_dmb, kind='quadratic',
+                                                                             fill_value='extrapolate')
+
+    def bulge_frac(self, mstar, redz=None, **kwargs):
+        mm = np.minimum(np.asarray(mstar, dtype=float) / self._mstar_char, 1.0)
+        flo, fhi = self._bulge_frac_lo, self._bulge_frac_hi
+        frac = flo + (fhi - flo) / (1.0 + ((1.0 / mm) - 1.0) ** self._width_dex)
+        return np.where((mm >= 1.0) | (frac > fhi), fhi, frac)
+
+    def mstar_from_mbulge(self, mbulge, redz=None, **kwargs):
+        mbulge = np.asarray(mbulge, dtype=float)
+        mstar = mbulge / self._bulge_frac_hi                    # right wherever this lands above the characteristic mass
+        below = (mstar / self._mstar_char) < 1.0
+        return np.where(below, self._interp_mstar_from_mbulge(mbulge), mstar)
+
+    def dmstar_dmbulge(self, mbulge, redz=None, **kwargs):
+        mbulge = np.asarray(mbulge, dtype=float)
+        below = (mbulge / self._mstar_char) < self._bulge_frac_hi
+        return np.where(below, self._interp_dmstar_dmbulge_from_mbulge(mbulge), 1.0 / self._bulge_frac_hi)
+
+    def _kernel_tables(self):
+        """The two interpolants as piecewise quadratics for the density kernel: ``(breaks (n+1,), coef (3, n))`` each,
+        value = c0 dx^2 + c1 dx + c2 with dx = x - breaks[i]; first / last piece extrapolate, as interp1d does."""
+        out = []
+        for itp in (self._interp_mstar_from_mbulge, self._interp_dmstar_dmbulge_from_mbulge):
+            spl = itp._spline                                   # scipy BSpline, k = 2
+            knots = np.unique(spl.t)                            # piece boundaries (the end knots are repeated)
+            left = knots[:-1]
+            # Taylor coefficients of each quadratic piece at its left end (evaluated just inside the piece)
+            mid = 0.5 * (left + knots[1:])
+            d2 = np.ravel(spl(mid, nu=2))
+            d1 = np.ravel(spl(mid, nu=1)) - d2 * (mid - left)
+            d0 = np.ravel(spl(mid)) - d1 * (mid - left) - 0.5 * d2 * (mid - left) ** 2
+            out.append((np.ascontiguousarray(knots), np.ascontiguousarray(np.stack([0.5 * d2, d1, d0]))))
+        return out
 
 
 # ---- M-Mbulge relations (host_relations.py:334-799)

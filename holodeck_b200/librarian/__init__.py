@@ -23,13 +23,19 @@ from holodeck_b200.librarian import lib_tools   # noqa: E402
 from holodeck_b200.librarian.lib_tools import (   # noqa: E402,F401
     _Param_Space, _Param_Dist, PD_Uniform, PD_Uniform_Log, PD_Normal, run_model,
 )
-from holodeck_b200.librarian import param_spaces_classic, combine   # noqa: E402,F401
+from holodeck_b200.librarian import recipes, param_spaces_classic, combine   # noqa: E402,F401
 from holodeck_b200.librarian.param_spaces_classic import (   # noqa: E402,F401
     PS_Classic_Phenom_Uniform, PS_Classic_Phenom_Astro_Extended, PS_Classic_GWOnly_Uniform,
 )
+
+from holodeck_b200.librarian import param_spaces   # noqa: E402
+from holodeck_b200.librarian.param_spaces import PS_Test, PS_Astro_Strong_All, PS_Astro_Strong_Hard   # noqa: E402,F401
 
 param_spaces_dict = {
     "PS_Classic_Phenom_Uniform": PS_Classic_Phenom_Uniform,
     "PS_Classic_Phenom_Astro_Extended": PS_Classic_Phenom_Astro_Extended,
     "PS_Classic_GWOnly_Uniform": PS_Classic_GWOnly_Uniform,
+    "PS_Test": PS_Test,
+    "PS_Astro_Strong_All": PS_Astro_Strong_All,
+    "PS_Astro_Strong_Hard": PS_Astro_Strong_Hard,
 }

@@ -68,19 +68,28 @@ def run_sam_at_pspace_params(args, space, pnum, params, writer=None):
         elif not args.recreate:
             return True, sim_fname
     try:
-        sam, hard = space.model_for_params(params)
-        data = lib_tools.run_model(
-            sam, hard,
-            pta_dur=args.pta_dur, nfreqs=args.nfreqs, nreals=args.nreals, nloudest=args.nloudest,
-            gwb_flag=args.gwb_flag, singles_flag=args.ss_flag, details_flag=False, params_flag=args.params_flag,
-            log=log, seed=_sample_seed(args.seed, pnum), device=writer is not None,
-        )
+        data = _run_model(args, space, pnum, params, device=writer is not None)
         rv = True
     except Exception as err:   # noqa: BLE001  (same catch-all as the reference)
         log.exception(f"`run_model` FAILED on {pnum=}\n")
         log.exception(err)
         rv = False
         data = dict(fail=str(err))
+    return _record(args, space, pnum, params, rv, data, writer, sim_fname)
+
+
+def _run_model(args, space, pnum, params, device, deferred=None):
+    sam, hard = space.model_for_params(params)
+    return lib_tools.run_model(
+        sam, hard,
+        pta_dur=args.pta_dur, nfreqs=args.nfreqs, nreals=args.nreals, nloudest=args.nloudest,
+        gwb_flag=args.gwb_flag, singles_flag=args.ss_flag, details_flag=False, params_flag=args.params_flag,
+        log=args.log, seed=_sample_seed(args.seed, pnum), device=device, deferred=deferred,
+    )
+
+
+def _record(args, space, pnum, params, rv, data, writer, sim_fname):
+    """hand a finished (or failed) sample to the file plane"""
     if writer is not None:
         if rv:
             writer.submit(pnum, data)
@@ -113,14 +122,18 @@ def _check_config(output, config, resume_ok=True):
 
 def run_library(space, output, nreals=DEF_NUM_REALS, nfreqs=DEF_NUM_FBINS, nloudest=DEF_NUM_LOUDEST,
                 pta_dur=DEF_PTA_DUR, gwb_flag=True, ss_flag=True, params_flag=False, recreate=False, seed=None,
-                log=None, indices=None, streaming=True, sim_files=False, param_space_name=None, workers=1):
+                log=None, indices=None, streaming=True, sim_files=False, param_space_name=None, workers=1, pipeline=True):
     """Generate this rank's share of the library; returns ``(num_done, failures)``.
 
     ``seed`` must be the same on every rank (``main`` broadcasts it): it fixes the sample permutation.
     ``workers``: host threads per rank, each driving its own CUDA stream.  A sample is ~10 ms of kernels plus a few
     ms of host work (model construction, launches, the overflow check of the loudest split, which synchronises);
     with two samples in flight the host work of one hides behind the kernels of the other and the kernels of the
-    two streams fill each other's tails.  Results do not depend on it (every sample has its own seed)."""
+    two streams fill each other's tails.  Results do not depend on it (every sample has its own seed).  Measured
+    on B200: no gain at one rank and a large loss at eight (the threads fight over the interpreter lock), hence the
+    default of one; what hides the host work instead is ``pipeline`` (streaming mode only): a sample's kernels are
+    enqueued without waiting for its overflow / sanity flags, which are looked at after the NEXT sample has been
+    enqueued (``single_sources.DeferredChecks``)."""
     from holodeck_b200 import utils
     from holodeck_b200.constants import YR
     rank, size = dist.world()
@@ -167,6 +180,62 @@ def run_library(space, output, nreals=DEF_NUM_REALS, nfreqs=DEF_NUM_FBINS, nloud
     for sim_num in indices:
         todo.put(int(sim_num))
 
+    def count(rv):
+        with lock:
+            if rv is False:
+                state["failures"] += 1
+            state["done"] += 1
+            if (MAX_FAILURES is not None) and (state["failures"] > MAX_FAILURES):
+                err = f"Failed {state['failures']} times on rank:{rank}!"
+                log.exception(err)
+                raise RuntimeError(err)
+
+    def finalize(pending):
+        """second half of a pipelined sample: look at its device flags (this is where the host waits for the GPU),
+        redo it synchronously in the rare overflow case, hand it to the writer"""
+        sim_num, params, data, checks, err = pending
+        rv = err is None
+        if rv:
+            try:
+                if checks.overflow():
+                    data = _run_model(args, space, sim_num, params, device=True)      # larger head, synchronous
+                else:
+                    checks.verify()
+            except Exception as ee:   # noqa: BLE001
+                err, rv = ee, False
+        if not rv:
+            log.exception(f"`run_model` FAILED on pnum={sim_num}\n")
+            log.exception(err)
+            data = dict(fail=str(err))
+        _record(args, space, sim_num, params, rv, data, writer, lib_tools._get_sim_fname(args.output_sims, sim_num))
+        count(rv)
+
+    def pipelined():
+        """One model behind: the kernels of sample i are enqueued without waiting (`DeferredChecks`), then sample
+        i-1 is finalised -- so the host work of building and launching a model (a few ms) runs while the GPU is still
+        drawing the previous one, instead of after it."""
+        from holodeck_b200 import single_sources
+        pending = None
+        while True:
+            try:
+                sim_num = todo.get_nowait()
+            except queue.Empty:
+                break
+            if writer.store.is_done(sim_num) and not args.recreate:
+                count(True)
+                continue
+            params = space.param_dict(sim_num)
+            checks = single_sources.DeferredChecks()
+            try:
+                cur = (sim_num, params, _run_model(args, space, sim_num, params, device=True, deferred=checks), checks, None)
+            except Exception as ee:   # noqa: BLE001
+                cur = (sim_num, params, None, None, ee)
+            if pending is not None:
+                finalize(pending)
+            pending = cur
+        if pending is not None:
+            finalize(pending)
+
     def one_sample(sim_num):
         params = space.param_dict(sim_num)
         rv, _ = run_sam_at_pspace_params(args, space, sim_num, params, writer=writer)
@@ -194,11 +263,13 @@ def run_library(space, output, nreals=DEF_NUM_REALS, nfreqs=DEF_NUM_FBINS, nloud
                 one_sample(sim_num)
 
     nworkers = max(1, int(workers))
+    have_cuda = False
     try:
         import torch
-        if not torch.cuda.is_available():
-            nworkers = 1
+        have_cuda = torch.cuda.is_available()
     except Exception:   # noqa: BLE001
+        pass
+    if not have_cuda:
         nworkers = 1
     t_first = None
     try:
@@ -209,6 +280,8 @@ def run_library(space, output, nreals=DEF_NUM_REALS, nfreqs=DEF_NUM_FBINS, nloud
             with concurrent.futures.ThreadPoolExecutor(nworkers) as pool:
                 for fut in [pool.submit(drain, True) for _ in range(nworkers)]:
                     fut.result()
+        elif pipeline and writer is not None and have_cuda and (ss_flag or params_flag):
+            pipelined()
         else:
             drain(False)
     finally:
@@ -243,6 +316,7 @@ def main(argv=None):
                     help="reference file plane only: synchronous per-sample .npz, merged by sam_lib_combine")
     ap.add_argument('--no-combine', action='store_true', default=False)
     ap.add_argument('--workers', type=int, default=1, help="host threads (CUDA streams) per rank; see run_library")
+    ap.add_argument('--no-pipeline', action='store_true', default=False, help="wait for every sample before starting the next")
     args = ap.parse_args(argv)
     dist.init()
     rank, size = dist.world()
@@ -254,7 +328,7 @@ def main(argv=None):
                               pta_dur=args.pta_dur, gwb_flag=args.gwb_flag, ss_flag=args.ss_flag,
                               params_flag=args.params_flag, recreate=args.recreate, seed=seed,
                               streaming=not args.no_streaming, sim_files=args.sim_files or args.no_streaming,
-                              param_space_name=args.param_space, workers=args.workers)
+                              param_space_name=args.param_space, workers=args.workers, pipeline=not args.no_pipeline)
     loop_s = dist.max_over_ranks(run_library.last_loop_s)
     first_s = run_library.last_first_sample_s or 0.0
     steady_s = dist.max_over_ranks(run_library.last_loop_s - first_s)

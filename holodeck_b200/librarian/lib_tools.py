@@ -235,6 +235,7 @@ def run_model(
     sam, hard,
     pta_dur=DEF_PTA_DUR, nfreqs=DEF_NUM_FBINS, nreals=DEF_NUM_REALS, nloudest=DEF_NUM_LOUDEST,
     gwb_flag=True, singles_flag=True, details_flag=False, params_flag=False, log=None, *, seed=None, device=False,
+    deferred=None,
 ):
     """Run the given SAM + hardening model to produce GW signals (``lib_tools.py:714-842``).
 
@@ -244,7 +245,8 @@ def run_model(
     ``details_flag`` adds ``static_binary_density, number, redz_final, gwb_params, num_params, gwb_mtot_redz_final,
     num_mtot_redz_final`` (``_calc_model_details``, K7).  Keyword-only additions: ``seed``; ``device=True`` leaves
     ``hc_ss, hc_bg, sspar, bgpar, gwb`` on the GPU as CUDA tensors (the streaming library writer copies them out
-    asynchronously, ``librarian/stream.py``).
+    asynchronously, ``librarian/stream.py``); ``deferred`` (a ``single_sources.DeferredChecks``, with ``device=True``)
+    postpones every host-side look at a device flag, so the call returns with its kernels still in flight.
     """
     from holodeck_b200.sams import sam_cyutils
     from holodeck_b200 import gravwaves, single_sources
@@ -295,6 +297,7 @@ def run_model(
         vals = single_sources.ss_gws_redz(
             edges, use_redz, number, realize=nreals, loudest=nloudest, params=params_flag,
             seed=None if sub is None else int(sub[0]), _precomputed=strain, device=bool(device),
+            _deferred=deferred if device else None,
             _gwb=(nreals, None if sub is None else int(sub[1])) if gwb_flag else None,
         )
         if gwb_flag:

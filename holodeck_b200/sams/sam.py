@@ -216,14 +216,27 @@ class Semi_Analytic_Model:
             for ii, vv in enumerate(gmt._kernel_params()):
                 par.gmt[ii] = vv
 
-        if not isinstance(mmb, host_relations.MMBulge_Standard) or not isinstance(mmb._bulge_frac, host_relations.BF_Constant):
+        bfrac = mmb._bulge_frac
+        if type(mmb) not in (host_relations.MMBulge_Standard, host_relations.MMBulge_KH2013, host_relations.MMBulge_MM2013) or \
+                type(bfrac) not in (host_relations.BF_Constant, host_relations.BF_Sigmoid):
             raise NotImplementedError(
-                f"mmbulge {mmb!r}: only power-law `MMBulge_Standard` relations with `BF_Constant` bulge fractions "
-                "are fused into the CUDA density kernel (SURVEY.md section 2a row 6).")
+                f"mmbulge {mmb!r}: only the power-law `MMBulge_Standard` relations with `BF_Constant` or `BF_Sigmoid` "
+                "bulge fractions are fused into the CUDA density kernel (SURVEY.md section 2a row 6).")
         par.mmb[0] = mmb._mamp
         par.mmb[1] = mmb._mplaw
         par.mmb[2] = mmb._mref
-        par.mmb[3] = mmb._bulge_frac.bulge_frac()
+        self._bf_tables_host = None
+        if isinstance(bfrac, host_relations.BF_Constant):
+            par.bf_kind = 0
+            par.mmb[3] = bfrac.bulge_frac()
+        else:
+            par.bf_kind = 1
+            (x0, c0), (x1, c1) = bfrac._kernel_tables()
+            assert x0.size == x1.size
+            par.bf_n = int(x0.size - 1)
+            for ii, vv in enumerate((bfrac._bulge_frac_lo, bfrac._bulge_frac_hi, bfrac._mstar_char, bfrac._width_dex)):
+                par.bf[ii] = vv
+            self._bf_tables_host = np.concatenate([x0, c0.ravel(), x1, c1.ravel()])
         par.hubble_time = cosmo.hubble_time
         par.om0 = cosmo.Om0
         par.age_universe = utils._AGE_UNIVERSE_GYR * holo.constants.GYR
@@ -241,8 +254,9 @@ class Semi_Analytic_Model:
         has_gmt = self._gmt is not None
         gmt_time = _lib.empty((M, Q, Z)) if has_gmt else None
         zprime = _lib.empty((M, Q, Z)) if has_gmt else None
+        bf_tab = None if self._bf_tables_host is None else _lib.to_dev(self._bf_tables_host)
         rc = lib.holo_sam_density(_lib.ptr(mtot), _lib.ptr(mrat), _lib.ptr(redz), _lib.ptr(age_z), _lib.ptr(dtdz_z),
-                                  M, Q, Z, C.byref(par), _lib.ptr(dens), _lib.ptr(gmt_time), _lib.ptr(zprime),
+                                  M, Q, Z, C.byref(par), _lib.ptr(bf_tab), _lib.ptr(dens), _lib.ptr(gmt_time), _lib.ptr(zprime),
                                   _lib.stream())
         _lib.check(rc, "static_binary_density")
         if has_gmt:

@@ -304,8 +304,13 @@ def add_scatter_to_masses(mtot, mrat, dens, scatter, refine=4, log=None, *, _def
     wkey = ("weights", float(scatter))
     if wkey not in gg:
         dist = scipy.stats.norm(loc=0.0, scale=scatter)
-        ww = _get_rolled_weights(gg["mgrid_log10"], dist)
-        gg[wkey] = _lib.to_dev(np.ascontiguousarray((ww @ ww).T))
+        ww = _lib.to_dev(_get_rolled_weights(gg["mgrid_log10"], dist))
+        # (W W)^T on the device: a library samples a new scatter value for every model, and under torchrun
+        # (OMP_NUM_THREADS=1) this 364^3 product was 10 ms of single-threaded host BLAS per sample
+        stale = [kk for kk in gg if isinstance(kk, tuple) and kk[0] == "weights"]
+        for kk in stale[:-3]:
+            del gg[kk]                   # keep the few most recent ones only
+        gg[wkey] = torch.matmul(ww, ww).T.contiguous()
     w2t = gg[wkey]
 
     grad = _lib.empty((npts, 2, Z))

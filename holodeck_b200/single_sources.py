@@ -37,8 +37,29 @@ def _rank_order_flat(h2fdf):
     return torch.sort(key, stable=True).indices.to(torch.int32)
 
 
+class DeferredChecks:
+    """The host-side checks of one deferred `ss_gws_redz` call: device flags that are looked at later, at the caller's
+    next synchronisation point (`librarian.gen_lib` pipelines one model behind).  `verify()` raises what the
+    synchronous call would have raised; `overflow()` says whether the loudest split has to be redone with a larger
+    head (HOLO_ERR_OVERFLOW)."""
+
+    def __init__(self):
+        self.loudest_flags = []      # int32[2] views: event-bucket overflow, head too short
+        self.bad_redz = None         # strain kernel's `redz < 0 and != -1` flag (int32[1]) or None
+        self.bad_sspar = None        # bool tensor: sspar[3] < 0 and != -1
+
+    def overflow(self):
+        return any(bool(ff.any().item()) for ff in self.loudest_flags)
+
+    def verify(self):
+        if self.bad_redz is not None and int(self.bad_redz.item()) != 0:
+            raise ValueError("redz < 0 and !=-1 found in redz, in ss_gws_redz()")
+        if self.bad_sspar is not None and bool(self.bad_sspar.any().item()):
+            raise ValueError("check 1: sspar[3] values are negative and not -1 in sings.ss_gws_redz()")
+
+
 def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=None, r0=0, device=False,
-                _precomputed=None, _gwb=None):
+                _precomputed=None, _gwb=None, _deferred=None):
     """Strain of the `loudest` loudest single sources and of the background, per frequency and realization.
 
     Parameters mirror ``single_sources.ss_gws_redz`` (``single_sources.py:40-85``):
@@ -79,6 +100,9 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
     # while it reads the values (strains computed elsewhere are checked in separate passes); the flag is read after
     # the draws, whose call synchronises anyway, so the check costs no extra pass and no extra stall.
     def check_redz():
+        if _deferred is not None and strain.get("bad_redz") is not None:
+            _deferred.bad_redz = strain["bad_redz"]
+            return
         flag = strain.get("bad_redz")
         if (flag is not None and int(flag.item()) != 0) or \
                 (flag is None and bool(torch.any(torch.logical_and(redz_d < 0, redz_d != -1)))):
@@ -93,7 +117,8 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
         hc2ss, hc2bg, sspar, bgpar, *extra = cyutils.loudest_hc_and_par_from_sorted_redz(
             number_d, h2fdf, realize, loudest,
             mt, mr, rz, strain["zmid"], strain["dcom"], strain["sepa"], strain["angs"],
-            None, None, None, seed=seed, r0=r0, device=True, order=order, **gkw)
+            None, None, None, seed=seed, r0=r0, device=True, order=order,
+            _defer=None if _deferred is None else _deferred.loudest_flags, **gkw)
         check_redz()
         extra = tuple(host(torch.sqrt(ee)) for ee in extra)
         hc_ss = host(torch.sqrt(hc2ss))
@@ -102,14 +127,17 @@ def ss_gws_redz(edges, redz, number, realize, loudest=1, params=False, *, seed=N
         bgpar = host(bgpar)
         # check that all final redshifts are positive or -1
         bad = (sspar[3] < 0) & (sspar[3] != -1)
-        if bool(bad.any()):
+        if _deferred is not None and device:
+            _deferred.bad_sspar = bad
+        elif bool(bad.any()):
             err = int(bad.sum())
             err = f"check 1: {err} out of {int(np.prod(sspar[3].shape))} sspar[3] are negative and not -1 in sings.ss_gws_redz()"
             raise ValueError(err)
         return (hc_ss, hc_bg, sspar, bgpar) + extra
 
     hc2ss, hc2bg, *extra = cyutils.loudest_hc_from_sorted(number_d, h2fdf, realize, loudest, None, None, None,
-                                                          seed=seed, r0=r0, device=True, order=order, **gkw)
+                                                          seed=seed, r0=r0, device=True, order=order,
+                                                          _defer=None if _deferred is None else _deferred.loudest_flags, **gkw)
     check_redz()
     hc_ss = host(torch.sqrt(hc2ss))
     hc_bg = host(torch.sqrt(hc2bg))

@@ -77,7 +77,7 @@ typedef struct {
  * with the component callables fused in: GSMF_Schechter / GSMF_Double_Schechter
  * (sams/components.py:132-172, 315-329), GPF_Power_Law (:556-583), GMT_Power_Law (:646-675) +
  * zprime (:620-626) + utils.redz_after (utils.py:1772-1808), GMR_Illustris (:452-482),
- * MMBulge_Standard + BF_Constant (host_relations.py:745-771, 720-743, 483-512, 190-195).
+ * MMBulge_Standard + BF_Constant / BF_Sigmoid (host_relations.py:745-771, 720-743, 483-512, 190-195, 198-331).
  * Outputs are the PRE-scatter density, the galaxy-merger time and z' (all (M,Q,Z)).
  * `holo_zero_stalled` then applies sam.py:392-394.
  * --------------------------------------------------------------------------------------------- */
@@ -88,7 +88,8 @@ typedef struct {
     int gsmf_uses_mtot; /* sam.py:57-59 module switches */
     int gpf_uses_mtot;
     int gmt_uses_mtot;
-    int _pad0, _pad1;
+    int bf_kind;        /* bulge fraction: 0 = BF_Constant (mmb[3]), 1 = BF_Sigmoid (bf[], spline tables) */
+    int bf_n;           /* BF_Sigmoid: pieces per spline table */
     double gsmf[12];    /* kind 0: phi0, phiz, mchar0[g], mcharz, alpha0, alphaz
                            kind 1: phi1[3], phi2[3], log10_mstar[3], alpha1, alpha2, MSOL */
     double gpf[6];      /* frac_norm, mref[g], malpha, zbeta, qgamma, max_frac */
@@ -99,12 +100,16 @@ typedef struct {
     double hubble_time; /* [s] */
     double om0;
     double age_universe; /* [s]: utils._AGE_UNIVERSE_GYR * GYR, utils.py:46 */
+    double bf[4];       /* BF_Sigmoid (host_relations.py:198-331): frac_lo, frac_hi, mstar_char[g], width_dex */
 } holo_sam_params;
 
+/* `bf_tables` (device; NULL unless bf_kind == 1): the two quadratic interpolants BF_Sigmoid inverts its relation with
+ * (scipy interp1d(kind='quadratic') of mstar(mbulge) and dmstar/dmbulge(mbulge), host_relations.py:276-283) as
+ * piecewise polynomials, each [breaks (bf_n + 1) | c0 (bf_n) | c1 (bf_n) | c2 (bf_n)], value = c0 dx^2 + c1 dx + c2. */
 int holo_sam_density(const double* mtot, const double* mrat, const double* redz,
                      const double* age_z /* (Z,) cosmo.age(redz) [s] */,
                      const double* dtdz_z /* (Z,) cosmo.dtdz(redz) [s] */,
-                     int M, int Q, int Z, const holo_sam_params* par_host,
+                     int M, int Q, int Z, const holo_sam_params* par_host, const double* bf_tables,
                      double* dens, double* gmt_time /* may be NULL if !has_gmt */,
                      double* redz_prime /* may be NULL if !has_gmt */, void* stream);
 
@@ -268,11 +273,17 @@ typedef struct {
     int gwb_R;
     int64_t gwb_r0;
     uint64_t gwb_seed;
+    /* Deferred overflow check (ABI version 3).  By default `holo_loudest` reads its two overflow flags (event bucket
+     * overflow / head too short) back and is therefore synchronous.  With `defer_check` != 0 it returns as soon as the
+     * kernels are enqueued; the caller reads `int32 flags[2]` from the FIRST 8 bytes of `workspace` once the stream has
+     * got there and, if either is set, repeats the call with a larger `head_margin` / `bucket_cap`.  This lets a
+     * driver prepare and enqueue the next model while this one is still drawing (librarian/gen_lib.py). */
+    int defer_check;
 } holo_loudest_args;
 
 /* Bytes of scratch `holo_loudest` needs for these sizes (bucket_cap 0 = automatic). */
 int64_t holo_loudest_workspace_bytes(int variant, int64_t ncell, int F, int R, int L, int bucket_cap);
-/* Synchronous with respect to `stream` (it checks an overflow flag before returning). */
+/* Synchronous with respect to `stream` (it checks an overflow flag before returning) unless `defer_check` is set. */
 int holo_loudest(const holo_loudest_args* args_host, void* stream);
 
 /* _ss_bg_hc (cyutils.pyx:935-1014) and _ss_bg_hc_and_par (:1017-1178): L=1, arg-max by value.

@@ -354,8 +354,70 @@ def gmr_illustris(mtot, mrat, redz, **kw):
     return norm * mt * mp1t * qt
 
 
+class BFSigmoid:
+    """BF_Sigmoid host_relations.py:198-331: sigmoid bulge fraction with scipy-interp1d inverses (the reference's own
+    construction: grid :251-263, central differences :266-274, quadratic interpolants :276-283)."""
+    _INTERP_GRID_SIZE = 200
+    _DERIV_DELTA = 1.0e-6
+
+    def __init__(self, bulge_frac_lo=0.5, bulge_frac_hi=1.0, mstar_char_log10=11.0, width_dex=1.0):
+        self._bulge_frac_lo = bulge_frac_lo
+        self._bulge_frac_hi = bulge_frac_hi
+        self._mstar_char = (10.0 ** mstar_char_log10) * MSOL
+        self._width_dex = width_dex
+        mc = self._mstar_char
+        xx = np.log10(mc)
+        xbreak1 = xx - 0.5*width_dex
+        xbreak2 = xx + 0.5
+        _ms_lo = np.logspace(xbreak1 - 10.0, xbreak1, self._INTERP_GRID_SIZE//2, endpoint=False)
+        ms = np.logspace(xbreak1, xbreak2, self._INTERP_GRID_SIZE//2, endpoint=False)
+        _ms_hi = np.logspace(xbreak2, xbreak2 + 10.0, 10)
+        ms = np.concatenate([_ms_lo, ms, _ms_hi])
+        mb = self.mbulge_from_mstar(ms)
+        dd = self._DERIV_DELTA
+        ms_lo = ms * (1.0 - dd/2.0)
+        ms_hi = ms * (1.0 + dd/2.0)
+        mb_lo = self.mbulge_from_mstar(ms_lo)
+        mb_hi = self.mbulge_from_mstar(ms_hi)
+        dms_dmb = (ms_hi - ms_lo) / (mb_hi - mb_lo)
+        self._interp_mstar_from_mbulge = sp.interpolate.interp1d(mb, ms, kind='quadratic', fill_value='extrapolate')
+        self._interp_dmstar_dmbulge_from_mbulge = sp.interpolate.interp1d(mb, dms_dmb, kind='quadratic', fill_value='extrapolate')
+
+    def bulge_frac(self, mstar):
+        """host_relations.py:286-295"""
+        mm = mstar / self._mstar_char
+        steep = self._width_dex
+        flo = self._bulge_frac_lo
+        fhi = self._bulge_frac_hi
+        mm[mm > 1.0] = 1.0
+        frac = flo + (fhi - flo) / (1.0 + ((1.0 / mm) - 1.0)**steep)
+        frac[(mm >= 1.0) | (frac > fhi)] = fhi
+        return frac
+
+    def mbulge_from_mstar(self, mstar):
+        """_Bulge_Frac.mbulge_from_mstar host_relations.py:113-131"""
+        return mstar * self.bulge_frac(np.array(mstar, dtype=float))
+
+    def mstar_from_mbulge(self, mbulge):
+        """host_relations.py:297-308"""
+        fhi = self._bulge_frac_hi
+        mstar = np.ones_like(mbulge) * mbulge / fhi
+        sel = (mstar/self._mstar_char) < 1.0
+        mstar[sel] = self._interp_mstar_from_mbulge(mbulge[sel])
+        return mstar
+
+    def dmstar_dmbulge(self, mbulge):
+        """host_relations.py:310-321"""
+        fhi = self._bulge_frac_hi
+        dms_dmb = np.ones_like(mbulge) / fhi
+        sel = (mbulge/self._mstar_char) < fhi
+        dms_dmb[sel] = self._interp_dmstar_dmbulge_from_mbulge(mbulge[sel])
+        return dms_dmb
+
+
 class MMBulge:
-    """MMBulge_Standard / KH2013 / MM2013 with BF_Constant: host_relations.py:624-799, 166-195."""
+    """MMBulge_Standard / KH2013 / MM2013 with BF_Constant (or, `bulge_frac=BFSigmoid(...)`, BF_Sigmoid):
+    host_relations.py:624-799, 166-195, 198-331."""
     KINDS = {   # MASS_AMP_LOG10, MASS_PLAW, SCATTER_DEX, BULGE_MASS_FRAC   host_relations.py:640-644, 774-799
         'Standard': (8.17, 1.01, 0.3, 0.615),
         'KH2013': (8.69, 1.17, 0.28, 0.615),
@@ -382,11 +444,15 @@ class MMBulge:
         return self._mref * np.power(10.0, xx)
 
     def mstar_from_mbh(self, mbh):
-        """host_relations.py:768-771 ; BF_Constant.mstar_from_mbulge :190-192"""
+        """host_relations.py:768-771 ; BF_Constant.mstar_from_mbulge :190-192 / BF_Sigmoid :297-308"""
+        if isinstance(self._bfrac, BFSigmoid):
+            return self._bfrac.mstar_from_mbulge(np.array(self.mbulge_from_mbh(mbh), dtype=float))
         return self.mbulge_from_mbh(mbh) / self._bfrac
 
     def mbh_from_mstar(self, mstar):
         """host_relations.py:514-536"""
+        if isinstance(self._bfrac, BFSigmoid):
+            return self.mbh_from_mbulge(self._bfrac.mbulge_from_mstar(mstar))
         return self.mbh_from_mbulge(mstar * self._bfrac)
 
     def dmbulge_dmbh(self, mbulge):
@@ -396,6 +462,9 @@ class MMBulge:
 
     def dmstar_dmbh(self, mstar):
         """host_relations.py:483-512"""
+        if isinstance(self._bfrac, BFSigmoid):
+            mbulge = self._bfrac.mbulge_from_mstar(mstar)
+            return self._bfrac.dmstar_dmbulge(mbulge) * self.dmbulge_dmbh(mbulge)
         mbulge = mstar * self._bfrac
         dmstar_dmbulge = 1.0 / self._bfrac
         return dmstar_dmbulge * self.dmbulge_dmbh(mbulge)

@@ -28,13 +28,13 @@ static CyConsts to_cc(const holo_cy_consts& c) {
 extern "C" {
 
 void emu_sam_density(const double* mtot, const double* mrat, const double* redz, const double* age_z,
-                     const double* dtdz_z, int M, int Q, int Z, const holo_sam_params* par,
+                     const double* dtdz_z, int M, int Q, int Z, const holo_sam_params* par, const double* bf_tables,
                      double* dens, double* gmt_time, double* redz_prime) {
     for (int ii = 0; ii < M; ++ii)
         for (int jj = 0; jj < Q; ++jj)
             for (int kk = 0; kk < Z; ++kk) {
                 int64_t i = ((int64_t)ii * Q + jj) * Z + kk;
-                DensityOut o = density_point(*par, mtot[ii], mrat[jj], redz[kk], age_z[kk], dtdz_z[kk]);
+                DensityOut o = density_point(*par, bf_tables, mtot[ii], mrat[jj], redz[kk], age_z[kk], dtdz_z[kk]);
                 dens[i] = o.dens;
                 if (gmt_time) gmt_time[i] = o.gmt_time;
                 if (redz_prime) redz_prime[i] = o.redz_prime;

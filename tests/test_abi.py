@@ -35,7 +35,7 @@ def test_struct_layouts_match_the_header():
     from holodeck_b200 import _lib
     assert C.sizeof(_lib.CyConsts) == 4 * 8
     assert C.sizeof(_lib.CosmoParams) == (4 + 2 * _lib.GL_ORDER) * 8
-    assert C.sizeof(_lib.SamParams) == 8 * 4 + (12 + 6 + 5 + 11 + 4 + 3) * 8
+    assert C.sizeof(_lib.SamParams) == 8 * 4 + (12 + 6 + 5 + 11 + 4 + 3 + 4) * 8      # + bf[4] (BF_Sigmoid)
     assert _lib.LoudestArgs.number.offset % 8 == 0 and _lib.LoudestArgs.workspace_bytes.offset % 8 == 0
     cc = _lib.cy_consts()
     assert cc.gw_dadt_sep_const < 0 and abs(cc.kepler_const_sepa / 1.19128405e-3 - 1) < 1e-6

@@ -141,11 +141,48 @@ def test_emu_density(emu, golden_classic):
     sp.hubble_time, sp.om0, sp.age_universe = cosmo.hubble_time, cosmo.Om0, utils._AGE_UNIVERSE_GYR * GYR
     dens, gt, zp = [np.zeros((M, Q, Z)) for _ in range(3)]
     age_z, dtdz = cosmo.age(gg["redz"]), cosmo.dtdz(gg["redz"])
-    emu.emu_sam_density(P(gg["mtot"]), P(gg["mrat"]), P(gg["redz"]), P(age_z), P(dtdz), M, Q, Z, C.byref(sp), P(dens), P(gt), P(zp))
+    emu.emu_sam_density.argtypes = [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p] * 5
+    emu.emu_sam_density(P(gg["mtot"]), P(gg["mrat"]), P(gg["redz"]), P(age_z), P(dtdz), M, Q, Z, C.byref(sp), None,
+                        P(dens), P(gt), P(zp))
     dens[zp < 0] = 0.0
     assert np.array_equal(zp == -1, gg["redz_prime"] == -1)
     assert rel_err(dens, gg["dens"]) < 1e-11
     assert rel_err(gt, gg["gmt_time"]) < 1e-13
+
+
+def test_emu_density_bf_sigmoid(emu):
+    """K0 arithmetic with the sigmoid bulge fraction (`BF_Sigmoid`, host_relations.py:198-331; the M-Mbulge relation
+    of the `PS_Astro_Strong_*` spaces, param_spaces.py:246-257): the kernel evaluates the closed-form sigmoid and the
+    two quadratic interpolants scipy builds (handed over as piecewise polynomials by `Semi_Analytic_Model._kernel_params`)
+    -- against the oracle's restatement of the reference procedure (scipy interp1d), double-Schechter GSMF +
+    Illustris merger rate, three parameter sets incl. a narrow and a wide transition."""
+    from oracle import glue
+    from holodeck_b200 import sams, host_relations, cosmo
+    emu.emu_sam_density.argtypes = [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p] * 5
+    for (flo, fhi, mc, width) in ((0.4, 0.8, 11.0, 1.0), (0.1, 1.0, 10.5, 0.5), (0.35, 0.6, 11.4, 1.5)):
+        bf = host_relations.BF_Sigmoid(bulge_frac_lo=flo, bulge_frac_hi=fhi, mstar_char_log10=mc, width_dex=width)
+        mmb = host_relations.MMBulge_KH2013(mamp_log10=8.69, mplaw=1.17, scatter_dex=0.0, bulge_frac=bf)
+        sam = sams.Semi_Analytic_Model(gsmf=sams.GSMF_Double_Schechter, gmr=sams.GMR_Illustris, mmbulge=mmb, shape=(23, 19, 17))
+        par = sam._kernel_params()
+        assert par.bf_kind == 1 and par.bf_n > 100 and sam._bf_tables_host.size == 2 * (4 * par.bf_n + 1)
+        M, Q, Z = sam.shape
+        dens = np.zeros((M, Q, Z))
+        age_z, dtdz = cosmo.age(sam.redz), cosmo.dtdz(sam.redz)
+        emu.emu_sam_density(P(sam.mtot), P(sam.mrat), P(sam.redz), P(age_z), P(dtdz), M, Q, Z, C.byref(par),
+                            P(sam._bf_tables_host), P(dens), None, None)
+        oc = glue.OracleCosmo(closed_form=True)
+        omm = glue.MMBulge('KH2013', mamp_log10=8.69, mplaw=1.17, scatter_dex=0.0,
+                           bulge_frac=glue.BFSigmoid(bulge_frac_lo=flo, bulge_frac_hi=fhi, mstar_char_log10=mc, width_dex=width))
+        want = glue.static_binary_density(sam.mtot, sam.mrat, sam.redz, oc, glue.gsmf_double_schechter, omm,
+                                          gmr=glue.gmr_illustris, scatter=False)["dens"]
+        assert np.array_equal(dens == 0, want == 0)
+        assert rel_err(dens, want) < 1e-10, (flo, fhi, mc, width, rel_err(dens, want))
+        # ... and the host mirror of the class itself against the oracle's
+        ms = np.logspace(7.0, 13.0, 400) * 1.988409870698051e+33
+        assert rel_err(bf.bulge_frac(ms), omm._bfrac.bulge_frac(ms.copy())) < 1e-15
+        mb = bf.mbulge_from_mstar(ms)
+        assert rel_err(bf.mstar_from_mbulge(mb), omm._bfrac.mstar_from_mbulge(mb.copy())) < 1e-14
+        assert rel_err(bf.dmstar_dmbulge(mb), omm._bfrac.dmstar_dmbulge(mb.copy())) < 1e-14
 
 
 def test_emu_samplers_are_exact_poisson(emu):
