@@ -329,7 +329,7 @@ constexpr int BUILD_SW = 8;      // lanes per element table
 // The window is always NSCAN cells and the record / pool limits are fixed, so the pass boundaries -- and with
 // them the membership of the superposition groups -- never depend on how the realizations are tiled or on the
 // CTA size (the scans carry over from one round of THREADS cells to the next in cell order).
-template <int VARIANT, int THREADS>
+template <int VARIANT, int THREADS, int NSCAN_T = NSCAN>
 static __device__ __forceinline__ int stage_pass(const RealizeArgs& a, int64_t cb, int64_t c_hi, int f0, int nf, Rec* s_rec,
                                               double* s_w3, double* s_w4, double* s_gcum, unsigned long long* s_wsum,
                                               double* s_wlam, unsigned long long* s_tot, double* s_totlam
@@ -348,7 +348,7 @@ static __device__ __forceinline__ int stage_pass(const RealizeArgs& a, int64_t c
     int ncons = 0;
     unsigned long long carry = 0;
     double carry_lam = 0.0;
-    for (int sbase = 0; sbase < NSCAN; sbase += THREADS) {    // one or two rounds of THREADS cells
+    for (int sbase = 0; sbase < NSCAN_T; sbase += THREADS) {    // rounds of THREADS cells
         const int64_t c = cb + sbase + tid;
         const bool inrange = (c < c_hi);
         unsigned clsw = 0;            // CLS_* byte per frequency slot
@@ -984,6 +984,352 @@ realize_kernel(RealizeArgs a) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// QUAD form of the realization kernel for the parameter variant V_LOUD_PAR_REDZ (cyutils.pyx:1615-1767), the one
+// `sam.gwb(params=True)` and `librarian.run_model` use.
+//
+// The variant folds every draw into EIGHT sums per frequency (hc2 and hc2 times M, q, z, z_final, d_c, a, theta).  In
+// the general kernel above a thread owns one realization and all four frequencies of its CTA: 32 fp64 accumulators =
+// 64 registers per realization slot, so it runs ONE slot per thread (one dependency chain, 1.1 KB of spills, four
+// realization tiles at R = 1000 that each re-stage and re-build everything): 3.5x slower than the plain split.
+// Here a CTA works on ONE frequency and a thread owns a QUAD of four CONSECUTIVE realizations:
+//   * 4 slots x 8 sums = the same 64 accumulator registers now carry four lock-step dependency chains for the whole
+//     chunk, and one CTA carries 1024 realizations -- a single tile, one staging / table build per pass, at R = 1000;
+//   * the Philox block of a table draw is keyed on (element, quad): its four words are the four realizations of the
+//     quad, so the generator still costs a quarter of a block per draw;
+//   * the record's eight weights h, h M, ..., h theta are formed once per thread and shared by the four slots;
+//   * the staging window is 1024 cells (one frequency per cell: the same ~170 non-empty elements per pass as the
+//     256-cell window of the four-frequency kernels).
+// [A first form kept the four frequencies per CTA and walked them one after the other, adding the 32 sums of each
+//  frequency sub-pass to global partial sums: a quarter of its time went into those read-modify-writes and another
+//  quarter into replaying the pass's superposition group once per frequency.]
+// Realizations of a quad: global index 4 Q + u, Q = (r0 >> 2) + local quad; slots outside [r0, r0 + R) are masked, so
+// any partition of the realizations over launches / GPUs gives identical numbers.
+// -------------------------------------------------------------------------------------------------
+constexpr int QUAD_NSCAN = 1024;
+
+// words `sub .. sub + N - 1` of a quad's Philox block (sub is a multiple of N)
+template <int N>
+__device__ __forceinline__ void quad_words(const Philox4& b, int sub, uint32_t (&w)[N]) {
+    if (N == 4) {
+#pragma unroll
+        for (int u = 0; u < N; ++u) w[u] = b.v[u];
+    } else if (N == 2) {
+        w[0] = sub ? b.v[2] : b.v[0];
+        w[N - 1] = sub ? b.v[3] : b.v[1];
+    } else {
+        w[0] = sub == 0 ? b.v[0] : (sub == 1 ? b.v[1] : (sub == 2 ? b.v[2] : b.v[3]));
+    }
+}
+
+// QUAD = realizations of a quad carried by ONE thread: 4 (a CTA of 256 threads carries 1024 realizations), or -- small
+// realization counts: library samples -- 2 or 1, so that the draws still spread over the warps of the CTA; the 4 / QUAD
+// threads of a quad then each compute the quad's Philox block and use their own words of it (the random numbers, and
+// with them every result, do not depend on QUAD).
+template <int QUAD, int THREADS, bool FUSED>
+__global__ void __launch_bounds__(THREADS, QUAD == 1 ? 3 : 2)
+realize_quad_kernel(RealizeArgs a) {
+    constexpr int VARIANT = V_LOUD_PAR_REDZ;
+    constexpr int NACC = nacc_of(VARIANT);
+    constexpr int NREC = nrec_of(NACC);
+    __shared__ __align__(16) Rec s_rec[NREC];
+    __shared__ double s_w3[NREC][3];
+    __shared__ double s_w4[NREC][4];
+    __shared__ double s_gcum[NREC];
+    __shared__ unsigned short s_plist[NREC];
+    __shared__ unsigned long long s_wsum[RZ_THREADS / 32];
+    __shared__ double s_wlam[RZ_THREADS / 32];
+    __shared__ unsigned long long s_tot;
+    __shared__ double s_totlam;
+    __shared__ int s_np;
+    __shared__ int s_gspec[3];
+    extern __shared__ __align__(16) uint32_t s_pool[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarp = THREADS / 32;
+    int f = blockIdx.x, chunk_id = blockIdx.y;          // ONE frequency per CTA
+    if (a.order != nullptr) {
+        const int item = a.order[blockIdx.y * gridDim.x + blockIdx.x];
+        f = item % (int)gridDim.x;
+        chunk_id = item / (int)gridDim.x;
+    }
+    const uint32_t fk = (uint32_t)(f + a.f_key0);       // global frequency index (Philox counter)
+    const int64_t c_lo = (int64_t)chunk_id * a.chunk;
+    int64_t c_hi = c_lo + a.chunk;
+    if (c_hi > a.ncell) c_hi = a.ncell;
+    const bool supplied = a.counts != nullptr;
+
+    // ---- the thread's quad (and, for QUAD < 4, its part of it: slots `sub * QUAD + u`)
+    constexpr int TPQ = 4 / QUAD;
+    const int tg = blockIdx.z * THREADS + tid;
+    const int q = tg / TPQ, sub = (tg % TPQ) * QUAD;
+    const int offL = (int)(a.r0 & 3), nqL = (a.R + offL + 3) >> 2;
+    const int offG = FUSED ? (int)(a.r0g & 3) : 0, nqG = FUSED ? ((a.Rg + offG + 3) >> 2) : 0;
+    const bool gq = FUSED && q >= nqL;                  // a quad of fused background (GWB) realizations
+    const bool liveq = q < nqL + nqG;
+    const int qq = gq ? q - nqL : q;
+    const int rbase = 4 * qq - (gq ? offG : offL) + sub;   // local realization of slot 0 (slots with r < 0 or >= Rme are masked)
+    const int Rme = gq ? a.Rg : a.R;
+    const uint32_t quad_global = (uint32_t)(((gq ? a.r0g : a.r0) >> 2) + qq);
+    const uint32_t k0 = gq ? a.k0g : a.k0, k1 = gq ? a.k1g : a.k1;
+    const uint32_t stream = gq ? (uint32_t)STREAM_GWB : (uint32_t)STREAM_LOUD;
+    bool valid[QUAD];
+    DrawKey kk[QUAD];
+#pragma unroll
+    for (int u = 0; u < QUAD; ++u) {
+        valid[u] = liveq && (rbase + u >= 0) && (rbase + u < Rme);
+        kk[u].k0 = k0; kk[u].k1 = k1; kk[u].stream = stream;
+        kk[u].real = 4u * quad_global + (uint32_t)(sub + u);
+    }
+    double acc[QUAD][NACC];
+#pragma unroll
+    for (int u = 0; u < QUAD; ++u)
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[u][k] = 0.0;
+
+    int64_t cb = c_lo;
+    HOLO_PHASE_DECL
+    while (cb < c_hi) {
+        const int ncons = stage_pass<VARIANT, THREADS, QUAD_NSCAN>(a, cb, c_hi, f, 1, s_rec, &s_w3[0][0], &s_w4[0][0], s_gcum, s_wsum,
+                                                                   s_wlam, &s_tot, &s_totlam
+#ifdef HOLO_PHASE_CLOCKS
+                                                                   , ph_last
+#endif
+                                                                   );
+        const uint32_t pass_id = (uint32_t)cb;
+        cb += ncons;
+        __syncthreads();
+        HOLO_PHASE_MARK(0)
+        const int nmain = (int)(s_tot & 2047u), ngrp = (int)((s_tot >> 11) & 2047u);
+        const double glam_tot = s_totlam;
+        if (!supplied) {
+            constexpr int NSUB = 32 / BUILD_SW;
+            const int sub = lane / BUILD_SW, sl = lane % BUILD_SW;
+            for (int base = warp * NSUB; base < nmain; base += nwarp * NSUB) {
+                const int i = base + sub;
+                const bool act = (i < nmain) && (((s_rec[i < nmain ? i : 0].meta >> 2) & 7u) == CLS_TABLE);
+                const Rec& rec = s_rec[act ? i : 0];
+                build_table_sub<BUILD_SW>(rec.lam, s_pool + rec.toff, (int)rec.kmin, (int)((rec.meta >> 12) & 4095u), sl, act);
+            }
+            if (warp == nwarp - 1 && ngrp > 0) {
+                const TableSpec ts = table_spec(glam_tot);
+                build_table_sub<32>(glam_tot, s_pool + 1, ts.kmin, ts.W, lane, true);
+                if (lane == 0) { s_gspec[0] = ts.kmin; s_gspec[1] = ts.W; s_gspec[2] = 31 - __clz(ts.W); }
+            }
+            if (warp == 0) {
+                int np = 0;         // PTRS records with prep_draw's b / vr (see the general kernel)
+                for (int base = 0; base < nmain; base += 32) {
+                    const int i = base + lane;
+                    const bool is = (i < nmain) && (((s_rec[i].meta >> 2) & 7u) == CLS_PTRS);
+                    const unsigned bal = __ballot_sync(0xffffffffu, is);
+                    if (is) {
+                        const int j = np + __popc(bal & ((1u << lane) - 1u));
+                        s_plist[j] = (unsigned short)i;
+                        FPrep pp;
+                        prep_draw(s_rec[i].lam, a.thresh, pp);
+                        s_gcum[NREC - 1 - j] = pp.a0;
+                        *reinterpret_cast<double*>(&s_rec[i].kmin) = pp.a1;
+                    }
+                    np += __popc(bal);
+                }
+                if (lane == 0) s_np = np;
+            }
+        }
+        __syncthreads();
+        HOLO_PHASE_MARK(1)
+        if (!liveq) continue;
+        // ---- phase A: the main records, four slots in lock-step
+        for (int i = 0; i < nmain; ++i) {
+            const Rec rec = s_rec[i];
+            const uint32_t meta = rec.meta;
+            const uint32_t cls = (meta >> 2) & 7u;
+            if (cls == CLS_PTRS) continue;
+            double n[QUAD];
+            if (supplied) {
+#pragma unroll
+                for (int u = 0; u < QUAD; ++u)
+                    n[u] = valid[u] ? a.counts[((int64_t)(rbase + u) * a.F + f) * a.ncell + rec.cell] : 0.0;
+            } else if (cls == CLS_TABLE) {
+                const Philox4 blk = quad_bits(k0, k1, stream, (uint32_t)rec.cell, fk, 0u, quad_global, PURPOSE_QUAD_HI);
+                uint32_t word[QUAD];
+                quad_words<QUAD>(blk, sub, word);
+                uint32_t qi[QUAD];
+                const int W = (int)((meta >> 12) & 4095u), lg = (int)((meta >> 8) & 15u);
+                table_ladder_n<QUAD>(s_pool, rec.toff, W, lg, word, qi);
+                bool amb = false;
+#pragma unroll
+                for (int u = 0; u < QUAD; ++u) {
+                    n[u] = (double)(int)(rec.kmin + (qi[u] - rec.toff));
+                    amb |= table_ambiguous(s_pool, rec.toff, W, qi[u], word[u]);
+                }
+                if (amb) {      // (prob. ~ 12 W 2^-32 per record: the low halves of the quad's uniforms)
+                    const Philox4 lo = quad_bits(k0, k1, stream, (uint32_t)rec.cell, fk, 0u, quad_global, PURPOSE_QUAD_LO);
+                    uint32_t low[QUAD];
+                    quad_words<QUAD>(lo, sub, low);
+#pragma unroll
+                    for (int u = 0; u < QUAD; ++u)
+                        if (table_ambiguous(s_pool, rec.toff, W, qi[u], word[u]))
+                            n[u] = table_resolve(rec.lam, s_pool + rec.toff, (int)rec.kmin, W, (int)(qi[u] - rec.toff), word[u], low[u]);
+                }
+            } else {        // CLS_NORMAL
+                const uint64_t idx = (uint64_t)(uint32_t)rec.cell * (uint64_t)a.F_key + (uint64_t)fk;
+#pragma unroll
+                for (int u = 0; u < QUAD; ++u) n[u] = draw_normal_lam(rec.lam, kk[u], idx);
+            }
+            // the eight weights of the record (shared by the four slots) and the fold of its draws
+            const double h = rec.h;
+            double hw[NACC];
+            hw[0] = h;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) hw[1 + k] = h * s_w3[i][k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hw[4 + k] = h * s_w4[i][k];
+            const bool head = (meta & META_HEAD) && !gq;
+#pragma unroll
+            for (int u = 0; u < QUAD; ++u) {
+                if (!valid[u]) continue;
+                if (head) {
+                    if (n[u] >= 1.0) push_event(a, f, rbase + u, rec.cell, n[u]);       // pyx:1727-1742
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) acc[u][k] += n[u] * hw[k];          // pyx:1745-1752
+                }
+            }
+        }
+        HOLO_PHASE_MARK(2)
+        if (supplied) continue;
+        // ---- the pass's superposition group (see draw_group in holo_rng.cuh), four slots in lock-step
+        if (ngrp > 0) {
+            const int gk = s_gspec[0], gW = s_gspec[1], glg = s_gspec[2];
+            uint32_t w0[QUAD], w1[QUAD], qc[QUAD];
+#pragma unroll
+            for (int u = 0; u < QUAD; ++u) {
+                const Philox4 gb = philox4x32_10(pass_id, fk | ((uint32_t)PURPOSE_PASS_COUNT << 28), kk[u].real, stream << 24, k0, k1);
+                w0[u] = gb.v[0];
+                w1[u] = gb.v[1];
+            }
+            table_ladder_n<QUAD>(s_pool, 1u, gW, glg, w0, qc);
+            int nev[QUAD], nmax = 0;
+#pragma unroll
+            for (int u = 0; u < QUAD; ++u) {
+                double ne = (double)(gk + (int)(qc[u] - 1u));
+                if (table_ambiguous(s_pool, 1u, gW, qc[u], w0[u]))
+                    ne = table_resolve(glam_tot, s_pool + 1, gk, gW, (int)(qc[u] - 1u), w0[u], w1[u]);
+                nev[u] = valid[u] ? (int)ne : 0;
+                nmax = nev[u] > nmax ? nev[u] : nmax;
+            }
+            uint32_t odd2[QUAD], odd3[QUAD];
+            for (int ev = 0; ev < nmax; ++ev) {
+                double v[QUAD];
+                if ((ev & 1) == 0) {
+#pragma unroll
+                    for (int u = 0; u < QUAD; ++u) {
+                        const Philox4 pb = philox4x32_10(pass_id, fk | ((uint32_t)PURPOSE_PASS_PICK << 28), kk[u].real,
+                                                         (stream << 24) | (uint32_t)(ev >> 1), k0, k1);
+                        v[u] = u53(pb.v[0], pb.v[1]) * glam_tot;
+                        odd2[u] = pb.v[2];
+                        odd3[u] = pb.v[3];
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < QUAD; ++u) v[u] = u53(odd2[u], odd3[u]) * glam_tot;
+                }
+                int base[QUAD];
+#pragma unroll
+                for (int u = 0; u < QUAD; ++u) base[u] = 0;
+                int len = ngrp;
+                while (len > 1) {
+                    const int half = len >> 1;
+#pragma unroll
+                    for (int u = 0; u < QUAD; ++u)
+                        if (s_gcum[base[u] + half - 1] <= v[u]) base[u] += half;
+                    len -= half;
+                }
+#pragma unroll
+                for (int u = 0; u < QUAD; ++u) {
+                    if (s_gcum[base[u]] <= v[u] && base[u] < ngrp - 1) base[u] += 1;
+                    if (ev >= nev[u]) continue;
+                    const int slot = NREC - 1 - base[u];
+                    const Rec rec = s_rec[slot];
+                    if ((rec.meta & META_HEAD) && !gq) {
+                        push_event(a, f, rbase + u, rec.cell, 1.0);
+                    } else {
+                        const double h = rec.h;
+                        acc[u][0] += h;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) acc[u][1 + k] += h * s_w3[slot][k];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[u][4 + k] += h * s_w4[slot][k];
+                    }
+                }
+            }
+        }
+        // ---- the PTRS records: every slot at its own pace, proposals side by side
+        const int np = s_np;
+        if (np > 0) {
+            int it[QUAD];
+            uint32_t trial[QUAD];
+#pragma unroll
+            for (int u = 0; u < QUAD; ++u) { it[u] = valid[u] ? 0 : np; trial[u] = 0u; }
+            for (;;) {
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < QUAD; ++u) any |= (it[u] < np);
+                if (!any) break;
+                double kq[QUAD], usq[QUAD], Vq[QUAD];
+                int dec[QUAD], ri[QUAD];
+#pragma unroll
+                for (int u = 0; u < QUAD; ++u) {
+                    const int j = it[u] < np ? it[u] : np - 1;
+                    ri[u] = s_plist[j];
+                    const double lam = s_rec[ri[u]].lam;
+                    const double b = s_gcum[NREC - 1 - j];
+                    const double vr = *reinterpret_cast<const double*>(&s_rec[ri[u]].kmin);
+                    const uint64_t idx = (uint64_t)(uint32_t)s_rec[ri[u]].cell * (uint64_t)a.F_key + (uint64_t)fk;
+                    dec[u] = ptrs_propose(lam, b, vr, element_bits(kk[u], idx, trial[u]), &kq[u], &usq[u], &Vq[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < QUAD; ++u) {
+                    if (it[u] >= np) continue;
+                    bool ok = dec[u] > 0;
+                    if (dec[u] == 0) ok = ptrs_decide(s_rec[ri[u]].lam, s_gcum[NREC - 1 - it[u]], usq[u], Vq[u], kq[u]);
+                    if (ok) {
+                        const Rec rec = s_rec[ri[u]];
+                        if ((rec.meta & META_HEAD) && !gq) {
+                            if (kq[u] >= 1.0) push_event(a, f, rbase + u, rec.cell, kq[u]);
+                        } else {
+                            const double nh = kq[u] * rec.h;
+                            acc[u][0] += nh;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) acc[u][1 + k] += nh * s_w3[ri[u]][k];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[u][4 + k] += nh * s_w4[ri[u]][k];
+                        }
+                        ++it[u];
+                        trial[u] = 0u;
+                    } else {
+                        ++trial[u];
+                    }
+                }
+            }
+        }
+        HOLO_PHASE_MARK(3)
+    }
+    // ---- the chunk's sums of this frequency
+#pragma unroll
+    for (int u = 0; u < QUAD; ++u) {
+        if (!valid[u]) continue;
+        const int r = rbase + u;
+        if (gq) {
+            a.partial_g[((int64_t)chunk_id * a.F + f) * a.Rg + r] = acc[u][0];
+        } else {
+            double* dst = a.partial + (((int64_t)chunk_id * a.F + f) * NACC) * a.R + r;
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) dst[(int64_t)k * a.R] = acc[u][k];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Launch order of the realization kernel: longest-processing-time-first list scheduling.
 // cost_kernel estimates the work of every (chunk, frequency group) item from the sampler classes of its elements
 // (a table draw = 16 units, a PTRS draw = 64, a member of a superposition group = 1: measured CTA durations follow
@@ -1000,7 +1346,7 @@ __device__ __forceinline__ int cost_bin(uint32_t c) {     // c >= 1
 }
 
 __global__ void __launch_bounds__(256)
-cost_kernel(const double* __restrict__ number, int64_t ncell, int F, int64_t chunk, int nfg, double thresh,
+cost_kernel(const double* __restrict__ number, int64_t ncell, int F, int64_t chunk, int nfg, int fgroup, double thresh,
             const int32_t* __restrict__ rank, const int32_t* __restrict__ kf, double head_weight,
             uint32_t* __restrict__ cost, uint32_t* __restrict__ hist) {
     extern __shared__ uint32_t s_cost[];     // (nfg,)
@@ -1021,7 +1367,7 @@ cost_kernel(const double* __restrict__ number, int64_t ncell, int F, int64_t chu
         // longer than their tables predict (0.6 ms per expected event per realization at 1024 realizations per CTA);
         // left unweighted they start late and ARE the tail of the kernel.  Overweighting only starts them earlier.
         if (rank != nullptr && rank[c_lo + e / F] < kf[f]) w += 32u + (uint32_t)(head_weight * (lam >= 1.0 ? 1.0 : lam));
-        atomicAdd(&s_cost[f / FGROUP], w);
+        atomicAdd(&s_cost[f / fgroup], w);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nfg; i += blockDim.x) {
@@ -1420,7 +1766,8 @@ static Plan make_plan(int64_t ncell, int F, int R, int variant) {
     p.rpt = rpt;
     p.threads = threads_for(rpt, R);
     p.ntiles = (R + p.threads * rpt - 1) / (p.threads * rpt);
-    p.nfg = (F + FGROUP - 1) / FGROUP;
+    // frequency items per chunk: groups of FGROUP, or -- quad kernel of the parameter variant -- single frequencies
+    p.nfg = variant == V_LOUD_PAR_REDZ ? F : (F + FGROUP - 1) / FGROUP;
     // The cell chunking must not depend on R (or on the realization tiling): per-chunk partial sums are
     // combined in a fixed order, so a fixed chunking makes hc2 bit-identical however the realizations
     // are partitioned over launches / GPUs (partials cost nchunk*F*NACC*R*8 bytes: 328 MB ... 2.6 GB at R = 1000).
@@ -1494,12 +1841,12 @@ static Layout carve(void* ws, int variant, int64_t ncell, int F, int R, int cap,
 
 // fills l.order (heaviest items first) on `st`
 static int plan_launch_order(const double* number, int64_t ncell, int F, double thresh, const int32_t* rank,
-                             const int32_t* kf, int R, const Plan& p, const Layout& l, cudaStream_t st) {
+                             const int32_t* kf, int R, const Plan& p, const Layout& l, cudaStream_t st, int fgroup = FGROUP) {
     const int per_cta = R < p.threads * p.rpt ? R : p.threads * p.rpt;     // realizations one CTA carries
     const double head_weight = 8.0 * per_cta;
     const int n = p.nchunk * p.nfg;
     HOLO_CUDA(cudaMemsetAsync(l.hist, 0, sizeof(uint32_t) * 2 * COST_BINS, st));
-    cost_kernel<<<p.nchunk, 256, sizeof(uint32_t) * p.nfg, st>>>(number, ncell, F, p.chunk, p.nfg, thresh, rank, kf, head_weight, l.cost, l.hist);
+    cost_kernel<<<p.nchunk, 256, sizeof(uint32_t) * p.nfg, st>>>(number, ncell, F, p.chunk, p.nfg, fgroup, thresh, rank, kf, head_weight, l.cost, l.hist);
     order_kernel<<<(n + 255) / 256, 256, 0, st>>>(l.cost, l.hist, l.hist + COST_BINS, n, l.order);
     holo::count_launches(2);
     return holo_check_launch("realization launch order");
@@ -1529,6 +1876,44 @@ template <int VARIANT, int RPT, int THREADS>
 static int launch_realize_rpt(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
     if (has_events(VARIANT) && ra.Rg > 0) return launch_realize_fused<VARIANT, RPT, THREADS, has_events(VARIANT)>(ra, p, st);
     return launch_realize_fused<VARIANT, RPT, THREADS, false>(ra, p, st);
+}
+
+template <int QN, bool FUSED>
+static int launch_quad_fused(const RealizeArgs& ra, const Plan& p, int nq, cudaStream_t st) {
+    const int nthreads = nq * (4 / QN);
+    dim3 grid(p.nfg, p.nchunk, (nthreads + RZ_THREADS - 1) / RZ_THREADS);
+    const size_t pool_bytes = sizeof(uint32_t) * pool_entries_of(V_LOUD_PAR_REDZ);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    HOLO_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        HOLO_CUDA(cudaFuncSetAttribute(realize_quad_kernel<QN, RZ_THREADS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
+        HOLO_CUDA(cudaFuncSetAttribute(realize_quad_kernel<QN, RZ_THREADS, FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    realize_quad_kernel<QN, RZ_THREADS, FUSED><<<grid, RZ_THREADS, pool_bytes, st>>>(ra); holo::count_launches(1);
+    return holo_check_launch("realize_quad_kernel");
+}
+
+// quads of realizations a launch of the quad kernel needs (loudest realizations, then the fused GWB ones)
+static int quad_count(const RealizeArgs& ra) {
+    const int nqL = (ra.R + (int)(ra.r0 & 3) + 3) >> 2;
+    const int nqG = ra.Rg > 0 ? ((ra.Rg + (int)(ra.r0g & 3) + 3) >> 2) : 0;
+    return nqL + nqG;
+}
+
+template <int QN>
+static int launch_quad_n(const RealizeArgs& ra, const Plan& p, int nq, cudaStream_t st) {
+    return ra.Rg > 0 ? launch_quad_fused<QN, true>(ra, p, nq, st) : launch_quad_fused<QN, false>(ra, p, nq, st);
+}
+
+static int launch_quad(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
+    const int nq = quad_count(ra);
+    // realizations per thread from the realization count, as `rpt_for` does for the plain kernels: a 256-thread CTA
+    // carries up to 1024 / 512 / 256 realizations
+    if (4 * nq > 2 * RZ_THREADS) return launch_quad_n<4>(ra, p, nq, st);
+    if (4 * nq > RZ_THREADS) return launch_quad_n<2>(ra, p, nq, st);
+    return launch_quad_n<1>(ra, p, nq, st);
 }
 
 template <int VARIANT>
@@ -1702,12 +2087,12 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     ra.fg_key0 = 0; ra.f_key0 = 0; ra.F_key = F;
     ra.Rg = Rg; ra.r0g = g->gwb_r0; ra.k0g = (uint32_t)g->gwb_seed; ra.k1g = (uint32_t)(g->gwb_seed >> 32);
     ra.partial_g = partial_g;
-    rc = plan_launch_order(g->number, ncell, F, ra.thresh, l.rank, l.kf, R, p, l, st);
+    rc = plan_launch_order(g->number, ncell, F, ra.thresh, l.rank, l.kf, R, p, l, st, v == V_LOUD_PAR_REDZ ? 1 : FGROUP);
     if (rc) return rc;
     ra.order = l.order;
     if (v == V_LOUD_PLAIN) rc = launch_realize<V_LOUD_PLAIN>(ra, p, st);
     else if (v == V_LOUD_PAR) rc = launch_realize<V_LOUD_PAR>(ra, p, st);
-    else rc = launch_realize<V_LOUD_PAR_REDZ>(ra, p, st);
+    else rc = launch_quad(ra, p, st);            // (launch_realize<V_LOUD_PAR_REDZ>: the one-slot form, kept for reference)
     if (rc) return rc;
 
     timer.mark();

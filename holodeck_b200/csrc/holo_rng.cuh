@@ -70,6 +70,8 @@ enum {
     PURPOSE_ELEMENT = 3,    // one block per (cell, f, realization, trial): PTRS / normal / TINY refinement
     PURPOSE_PASS_COUNT = 4, // event count of a pass's superposition group (draw_group), keyed on the pass
     PURPOSE_PASS_PICK = 5,  // member picks of the same group: two 53-bit uniforms per block
+    PURPOSE_QUAD_HI = 6,    // one block per (element, QUAD of four consecutive realizations): word u -> realization 4q + u
+    PURPOSE_QUAD_LO = 7,    // second block of the same quad: low halves of the 64-bit uniforms
 };
 
 struct DrawKey {
@@ -81,6 +83,13 @@ struct DrawKey {
 // block shared by the (up to 4) frequencies of group `fg` of cell `cell`
 HOLO_HD Philox4 group_bits(const DrawKey& k, uint32_t cell, uint32_t fg, int purpose) {
     return philox4x32_10(cell, fg | ((uint32_t)purpose << 28), k.real, k.stream << 24, k.k0, k.k1);
+}
+
+// block shared by the four consecutive realizations 4q .. 4q+3 of ONE element (cell, frequency slot `fi` of group
+// `fg`): the parameter variants of the realization kernel give a thread four realizations of one frequency at a time
+HOLO_HD Philox4 quad_bits(uint32_t k0, uint32_t k1, uint32_t stream, uint32_t cell, uint32_t fg, uint32_t fi, uint32_t quad,
+                          int purpose) {
+    return philox4x32_10(cell, fg | (fi << 24) | ((uint32_t)purpose << 28), quad, stream << 24, k0, k1);
 }
 
 // block private to grid element `idx` (= cell*F + f)

@@ -21,7 +21,7 @@ rz, dn = sam_cyutils.dynamic_binary_number_at_fobs(fobs_cents / 2.0, sam, hard, 
 edges = [sam.mtot, sam.mrat, sam.redz, fobs_edges / 2.0]
 strain = gravwaves._char_strain_sq(edges, rz, params=True, dnum=dn)
 number, h2fdf = strain["number"], strain["h2fdf"]
-names = ["staging", "table builds", "phase A (tables)", "group + PTRS", "barrier wait", "", "", ""]
+names = ["staging", "table builds", "phase A (tables)", "group + PTRS", "barrier wait", "flush (quad kernel)", "", ""]
 
 
 def report(tag, fn):
@@ -31,7 +31,7 @@ def report(tag, fn):
     fn(); torch.cuda.synchronize()
     lib.holo_debug_phase_clocks(buf, 1)
     tot = float(sum(buf))
-    print(tag, " ".join("%s %.1f%%" % (names[i], 100.0 * buf[i] / tot) for i in range(5)), " total CTA-cycles %.3e" % tot, flush=True)
+    print(tag, " ".join("%s %.1f%%" % (names[i], 100.0 * buf[i] / tot) for i in range(6)), " total CTA-cycles %.3e" % tot, flush=True)
 
 
 for R in [int(x) for x in sys.argv[1:]] or [1, 100, 1000]:

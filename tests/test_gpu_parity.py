@@ -203,6 +203,27 @@ def test_realizations_do_not_depend_on_partition(holo, golden_classic):
     assert np.array_equal(cyutils.sam_poisson_gwb(gg["number"], gg["h2fdf"], 600, seed=9), np.concatenate(quarters, axis=1))
 
 
+def test_parameter_variant_does_not_depend_on_partition(holo, golden_classic):
+    """The parameter variant (`loudest_hc_and_par_from_sorted_redz`) gives a thread a QUAD of four consecutive GLOBAL
+    realizations (Philox block keyed on (element, quad)): splits that cut through quads (r0 = 3, 10, 301) and the two
+    CTA sizes (<= 64 quads: 64 threads; more: 256) must reproduce the single launch bit for bit."""
+    from holodeck_b200 import cyutils
+    gg = golden_classic
+    ms, qs, zs = sort_indices(gg)
+    mt, mr, rz = [0.5 * (gg[kk][1:] + gg[kk][:-1]) for kk in ("mtot", "mrat", "redz")]
+    pars = (mt, mr, rz, gg["par_redz"], gg["par_dcom"], gg["par_sepa"], gg["par_angs"], ms, qs, zs)
+    for R, cuts in ((17, (0, 3, 10, 17)), (700, (0, 301, 700))):
+        full = cyutils.loudest_hc_and_par_from_sorted_redz(gg["number"], gg["h2fdf"], R, 3, *pars, seed=21)
+        parts = [cyutils.loudest_hc_and_par_from_sorted_redz(gg["number"], gg["h2fdf"], b - a, 3, *pars, seed=21, r0=a)
+                 for a, b in zip(cuts[:-1], cuts[1:])]
+        for ii, axis in enumerate((1, 1, 2, 2)):        # hc2ss (F,R,L), hc2bg (F,R), sspar (4,F,R,L), bgpar (7,F,R)
+            assert np.array_equal(full[ii], np.concatenate([pp[ii] for pp in parts], axis=axis), equal_nan=True), (R, ii)
+    # a global offset shifts the realizations, it does not redraw them
+    a = cyutils.loudest_hc_and_par_from_sorted_redz(gg["number"], gg["h2fdf"], 12, 2, *pars, seed=5, r0=0)
+    b = cyutils.loudest_hc_and_par_from_sorted_redz(gg["number"], gg["h2fdf"], 7, 2, *pars, seed=5, r0=5)
+    assert np.array_equal(a[1][:, 5:], b[1]) and np.array_equal(a[3][:, :, 5:], b[3], equal_nan=True)
+
+
 def _same_distribution(got, ref, nboot=40, nsig=7.0):
     """per-frequency 5 / 50 / 95 % quantiles of two independent samples agree within bootstrap Monte-Carlo error"""
     R = ref.shape[1]
