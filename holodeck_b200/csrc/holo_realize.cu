@@ -1025,15 +1025,25 @@ __device__ __forceinline__ void quad_words(const Philox4& b, int sub, uint32_t (
 // realization counts: library samples -- 2 or 1, so that the draws still spread over the warps of the CTA; the 4 / QUAD
 // threads of a quad then each compute the quad's Philox block and use their own words of it (the random numbers, and
 // with them every result, do not depend on QUAD).
-template <int QUAD, int THREADS, bool FUSED>
-__global__ void __launch_bounds__(THREADS, QUAD == 1 ? 3 : 2)
+#ifndef HOLO_QUAD_PLAIN_CTAS
+#define HOLO_QUAD_PLAIN_CTAS 3
+#endif
+// resident CTAs per SM the register allocation is asked to allow: one-sum variants 3 (80 registers), the
+// parameter variants 2 when a thread carries four slots of 4 or 8 sums
+__host__ __device__ constexpr int quad_min_ctas(int variant, int quad) {
+    return nacc_of(variant) == 1 ? HOLO_QUAD_PLAIN_CTAS : ((nacc_of(variant) == 4 ? quad < 4 : quad == 1) ? 3 : 2);
+}
+
+template <int VARIANT, int QUAD, int THREADS, bool FUSED>
+__global__ void __launch_bounds__(THREADS, quad_min_ctas(VARIANT, QUAD))
 realize_quad_kernel(RealizeArgs a) {
-    constexpr int VARIANT = V_LOUD_PAR_REDZ;
+    static_assert(!has_max(VARIANT), "the arg-max variants (ss_bg_hc) use the general kernel");
+    static_assert(!FUSED || has_events(VARIANT), "fused background slots exist in the loudest variants only");
     constexpr int NACC = nacc_of(VARIANT);
     constexpr int NREC = nrec_of(NACC);
     __shared__ __align__(16) Rec s_rec[NREC];
-    __shared__ double s_w3[NREC][3];
-    __shared__ double s_w4[NREC][4];
+    __shared__ double s_w3[NACC > 1 ? NREC : 1][3];
+    __shared__ double s_w4[NACC > 4 ? NREC : 1][4];
     __shared__ double s_gcum[NREC];
     __shared__ unsigned short s_plist[NREC];
     __shared__ unsigned long long s_wsum[RZ_THREADS / 32];
@@ -1071,7 +1081,7 @@ realize_quad_kernel(RealizeArgs a) {
     const int Rme = gq ? a.Rg : a.R;
     const uint32_t quad_global = (uint32_t)(((gq ? a.r0g : a.r0) >> 2) + qq);
     const uint32_t k0 = gq ? a.k0g : a.k0, k1 = gq ? a.k1g : a.k1;
-    const uint32_t stream = gq ? (uint32_t)STREAM_GWB : (uint32_t)STREAM_LOUD;
+    const uint32_t stream = (gq || !has_events(VARIANT)) ? (uint32_t)STREAM_GWB : (uint32_t)STREAM_LOUD;
     bool valid[QUAD];
     DrawKey kk[QUAD];
 #pragma unroll
@@ -1179,11 +1189,15 @@ realize_quad_kernel(RealizeArgs a) {
             const double h = rec.h;
             double hw[NACC];
             hw[0] = h;
+            if (NACC > 1) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) hw[1 + k] = h * s_w3[i][k];
+                for (int k = 0; k < 3; ++k) hw[(1 + k) < NACC ? 1 + k : 0] = h * s_w3[NACC > 1 ? i : 0][k];
+            }
+            if (NACC > 4) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) hw[4 + k] = h * s_w4[i][k];
-            const bool head = (meta & META_HEAD) && !gq;
+                for (int k = 0; k < 4; ++k) hw[(4 + k) < NACC ? 4 + k : 0] = h * s_w4[NACC > 4 ? i : 0][k];
+            }
+            const bool head = has_events(VARIANT) && (meta & META_HEAD) && !gq;
 #pragma unroll
             for (int u = 0; u < QUAD; ++u) {
                 if (!valid[u]) continue;
@@ -1250,15 +1264,19 @@ realize_quad_kernel(RealizeArgs a) {
                     if (ev >= nev[u]) continue;
                     const int slot = NREC - 1 - base[u];
                     const Rec rec = s_rec[slot];
-                    if ((rec.meta & META_HEAD) && !gq) {
+                    if (has_events(VARIANT) && (rec.meta & META_HEAD) && !gq) {
                         push_event(a, f, rbase + u, rec.cell, 1.0);
                     } else {
                         const double h = rec.h;
                         acc[u][0] += h;
+                        if (NACC > 1) {
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) acc[u][1 + k] += h * s_w3[slot][k];
+                            for (int k = 0; k < 3; ++k) acc[u][(1 + k) < NACC ? 1 + k : 0] += h * s_w3[NACC > 1 ? slot : 0][k];
+                        }
+                        if (NACC > 4) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[u][4 + k] += h * s_w4[slot][k];
+                            for (int k = 0; k < 4; ++k) acc[u][(4 + k) < NACC ? 4 + k : 0] += h * s_w4[NACC > 4 ? slot : 0][k];
+                        }
                     }
                 }
             }
@@ -1294,15 +1312,19 @@ realize_quad_kernel(RealizeArgs a) {
                     if (dec[u] == 0) ok = ptrs_decide(s_rec[ri[u]].lam, s_gcum[NREC - 1 - it[u]], usq[u], Vq[u], kq[u]);
                     if (ok) {
                         const Rec rec = s_rec[ri[u]];
-                        if ((rec.meta & META_HEAD) && !gq) {
+                        if (has_events(VARIANT) && (rec.meta & META_HEAD) && !gq) {
                             if (kq[u] >= 1.0) push_event(a, f, rbase + u, rec.cell, kq[u]);
                         } else {
                             const double nh = kq[u] * rec.h;
                             acc[u][0] += nh;
+                            if (NACC > 1) {
 #pragma unroll
-                            for (int k = 0; k < 3; ++k) acc[u][1 + k] += nh * s_w3[ri[u]][k];
+                                for (int k = 0; k < 3; ++k) acc[u][(1 + k) < NACC ? 1 + k : 0] += nh * s_w3[NACC > 1 ? ri[u] : 0][k];
+                            }
+                            if (NACC > 4) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) acc[u][4 + k] += nh * s_w4[ri[u]][k];
+                                for (int k = 0; k < 4; ++k) acc[u][(4 + k) < NACC ? 4 + k : 0] += nh * s_w4[NACC > 4 ? ri[u] : 0][k];
+                            }
                         }
                         ++it[u];
                         trial[u] = 0u;
@@ -1760,6 +1782,19 @@ struct Plan {
     int64_t chunk;
 };
 
+// Which variants run the quad kernel (one frequency per CTA): the parameter variants.  The one-sum variants (realised
+// GWB, plain loudest split) stay on the general four-frequency kernel: measured on B200 at the named grid the quad
+// form is no faster for them at R = 1000 (10.07 vs 10.06 ms) and slower at small R (R = 100: 4.8 vs 3.5 ms) -- their
+// accumulators already live in shared memory and four frequencies share a staging pass.  -DHOLO_PLAIN_QUAD builds
+// the quad form for them too (A/B comparison).
+static constexpr bool uses_quad_kernel(int variant) {
+#ifdef HOLO_PLAIN_QUAD
+    return !has_max(variant);
+#else
+    return variant == V_LOUD_PAR_REDZ || variant == V_LOUD_PAR;
+#endif
+}
+
 static Plan make_plan(int64_t ncell, int F, int R, int variant) {
     Plan p;
     const int rpt = rpt_for(variant, R);
@@ -1767,7 +1802,7 @@ static Plan make_plan(int64_t ncell, int F, int R, int variant) {
     p.threads = threads_for(rpt, R);
     p.ntiles = (R + p.threads * rpt - 1) / (p.threads * rpt);
     // frequency items per chunk: groups of FGROUP, or -- quad kernel of the parameter variant -- single frequencies
-    p.nfg = variant == V_LOUD_PAR_REDZ ? F : (F + FGROUP - 1) / FGROUP;
+    p.nfg = uses_quad_kernel(variant) ? F : (F + FGROUP - 1) / FGROUP;
     // The cell chunking must not depend on R (or on the realization tiling): per-chunk partial sums are
     // combined in a fixed order, so a fixed chunking makes hc2 bit-identical however the realizations
     // are partitioned over launches / GPUs (partials cost nchunk*F*NACC*R*8 bytes: 328 MB ... 2.6 GB at R = 1000).
@@ -1878,20 +1913,20 @@ static int launch_realize_rpt(const RealizeArgs& ra, const Plan& p, cudaStream_t
     return launch_realize_fused<VARIANT, RPT, THREADS, false>(ra, p, st);
 }
 
-template <int QN, bool FUSED>
+template <int VARIANT, int QN, bool FUSED>
 static int launch_quad_fused(const RealizeArgs& ra, const Plan& p, int nq, cudaStream_t st) {
     const int nthreads = nq * (4 / QN);
     dim3 grid(p.nfg, p.nchunk, (nthreads + RZ_THREADS - 1) / RZ_THREADS);
-    const size_t pool_bytes = sizeof(uint32_t) * pool_entries_of(V_LOUD_PAR_REDZ);
+    const size_t pool_bytes = sizeof(uint32_t) * pool_entries_of(VARIANT);
     static bool attr_set[64] = {};
     int dev = 0;
     HOLO_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        HOLO_CUDA(cudaFuncSetAttribute(realize_quad_kernel<QN, RZ_THREADS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
-        HOLO_CUDA(cudaFuncSetAttribute(realize_quad_kernel<QN, RZ_THREADS, FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HOLO_CUDA(cudaFuncSetAttribute(realize_quad_kernel<VARIANT, QN, RZ_THREADS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_bytes));
+        HOLO_CUDA(cudaFuncSetAttribute(realize_quad_kernel<VARIANT, QN, RZ_THREADS, FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    realize_quad_kernel<QN, RZ_THREADS, FUSED><<<grid, RZ_THREADS, pool_bytes, st>>>(ra); holo::count_launches(1);
+    realize_quad_kernel<VARIANT, QN, RZ_THREADS, FUSED><<<grid, RZ_THREADS, pool_bytes, st>>>(ra); holo::count_launches(1);
     return holo_check_launch("realize_quad_kernel");
 }
 
@@ -1902,18 +1937,19 @@ static int quad_count(const RealizeArgs& ra) {
     return nqL + nqG;
 }
 
-template <int QN>
+template <int VARIANT, int QN>
 static int launch_quad_n(const RealizeArgs& ra, const Plan& p, int nq, cudaStream_t st) {
-    return ra.Rg > 0 ? launch_quad_fused<QN, true>(ra, p, nq, st) : launch_quad_fused<QN, false>(ra, p, nq, st);
+    if (has_events(VARIANT) && ra.Rg > 0) return launch_quad_fused<VARIANT, QN, has_events(VARIANT)>(ra, p, nq, st);
+    return launch_quad_fused<VARIANT, QN, false>(ra, p, nq, st);
 }
 
+template <int VARIANT>
 static int launch_quad(const RealizeArgs& ra, const Plan& p, cudaStream_t st) {
     const int nq = quad_count(ra);
-    // realizations per thread from the realization count, as `rpt_for` does for the plain kernels: a 256-thread CTA
-    // carries up to 1024 / 512 / 256 realizations
-    if (4 * nq > 2 * RZ_THREADS) return launch_quad_n<4>(ra, p, nq, st);
-    if (4 * nq > RZ_THREADS) return launch_quad_n<2>(ra, p, nq, st);
-    return launch_quad_n<1>(ra, p, nq, st);
+    // realizations per thread from the realization count: a 256-thread CTA carries up to 1024 / 512 / 256 realizations
+    if (4 * nq > 2 * RZ_THREADS) return launch_quad_n<VARIANT, 4>(ra, p, nq, st);
+    if (4 * nq > RZ_THREADS) return launch_quad_n<VARIANT, 2>(ra, p, nq, st);
+    return launch_quad_n<VARIANT, 1>(ra, p, nq, st);
 }
 
 template <int VARIANT>
@@ -1994,10 +2030,10 @@ int realize_gwb_columns(const double* number, const double* h2fdf, int64_t ncell
     ra.fg_key0 = key_col0 / FGROUP; ra.f_key0 = key_col0; ra.F_key = key_cols > 0 ? key_cols : F;
     StageTimer timer(st);
     timer.mark();
-    int rc = plan_launch_order(number, ncell, F, ra.thresh, nullptr, nullptr, R, p, l, st);
+    int rc = plan_launch_order(number, ncell, F, ra.thresh, nullptr, nullptr, R, p, l, st, uses_quad_kernel(V_GWB) ? 1 : FGROUP);
     if (rc) return rc;
     ra.order = l.order;
-    rc = launch_realize<V_GWB>(ra, p, st);
+    rc = uses_quad_kernel(V_GWB) ? launch_quad<V_GWB>(ra, p, st) : launch_realize<V_GWB>(ra, p, st);
     if (rc) return rc;
     timer.mark();
     FinalArgs fa{};
@@ -2087,12 +2123,12 @@ int holo_loudest(const holo_loudest_args* g, void* stream) {
     ra.fg_key0 = 0; ra.f_key0 = 0; ra.F_key = F;
     ra.Rg = Rg; ra.r0g = g->gwb_r0; ra.k0g = (uint32_t)g->gwb_seed; ra.k1g = (uint32_t)(g->gwb_seed >> 32);
     ra.partial_g = partial_g;
-    rc = plan_launch_order(g->number, ncell, F, ra.thresh, l.rank, l.kf, R, p, l, st, v == V_LOUD_PAR_REDZ ? 1 : FGROUP);
+    rc = plan_launch_order(g->number, ncell, F, ra.thresh, l.rank, l.kf, R, p, l, st, uses_quad_kernel(v) ? 1 : FGROUP);
     if (rc) return rc;
     ra.order = l.order;
-    if (v == V_LOUD_PLAIN) rc = launch_realize<V_LOUD_PLAIN>(ra, p, st);
-    else if (v == V_LOUD_PAR) rc = launch_realize<V_LOUD_PAR>(ra, p, st);
-    else rc = launch_quad(ra, p, st);            // (launch_realize<V_LOUD_PAR_REDZ>: the one-slot form, kept for reference)
+    if (v == V_LOUD_PLAIN) rc = uses_quad_kernel(V_LOUD_PLAIN) ? launch_quad<V_LOUD_PLAIN>(ra, p, st) : launch_realize<V_LOUD_PLAIN>(ra, p, st);
+    else if (v == V_LOUD_PAR) rc = launch_quad<V_LOUD_PAR>(ra, p, st);
+    else rc = launch_quad<V_LOUD_PAR_REDZ>(ra, p, st);
     if (rc) return rc;
 
     timer.mark();
