@@ -67,8 +67,9 @@ def kernel(path):
 
 def metrics(paths):
     import json
-    short = {"realize_kernel": "loudest_draw", "dbn_2pwl_kernel": "dbn_2pwl", "bin_kernel": "integrate_strain",
-             "norm_2pwl_kernel": "norm_2pwl", "density_kernel": "density"}
+    short = {"realize_kernel": "loudest_draw", "realize_quad_kernel": "loudest_draw_params", "dbn_2pwl_kernel": "dbn_2pwl",
+             "bin_kernel": "integrate_strain", "norm_2pwl_kernel": "norm_2pwl", "density_kernel": "density",
+             "ct_gradients_kernel": "scatter_gradients", "ct_eval_kernel": "scatter_ct_eval"}
     res = {}
     for path in paths:
         out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
@@ -79,7 +80,7 @@ def metrics(paths):
             return float(rr[head.index(key)].replace(",", "")) if key in head else None
         for rr in rows[2:]:
             name = rr[head.index("Kernel Name")]
-            key = next((vv for kk, vv in short.items() if kk in name), None)
+            key = next((vv for kk, vv in sorted(short.items(), key=lambda kv: -len(kv[0])) if kk in name), None)
             if key is None:
                 continue
             units = rows[1]
@@ -95,6 +96,14 @@ def metrics(paths):
                 "ms_under_ncu": val(rr, "gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(
                     units[head.index("gpu__time_duration.sum")], 1.0),
             }
+    # the hash of the draw kernel's sources at capture time: bench.py flags a capture of an older kernel version
+    import hashlib
+    import pathlib
+    hh = hashlib.sha1()
+    for name in ("holo_realize.cu", "holo_rng.cuh"):
+        hh.update((pathlib.Path(__file__).resolve().parents[1] / "holodeck_b200" / "csrc" / name).read_bytes())
+    for ent in res.values():
+        ent["source_hash"] = hh.hexdigest()[:12]
     print(json.dumps(res, indent=1))
 
 
