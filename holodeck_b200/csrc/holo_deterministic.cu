@@ -233,12 +233,17 @@ dbn_2pwl_kernel(CyConsts cc, const double* __restrict__ fobs, int F, double sepa
     unsigned short* s_lo = reinterpret_cast<unsigned short*>(s_fobs + F);   // (Z, F)
     for (int kk = tid; kk < Z; kk += DBN_THREADS) {
         const double gmt = gmt_time[base + kk], az = s_zage[kk];
-        int lo = 0;
+        int lo = 0, hint = 0;
         double fprev = 0.0;
         for (int ff = 0; ff < F; ++ff) {
             const double ft = s_fobs[ff];
-            if (ff == 0 || ft < fprev) lo = dbn_2pwl_first_step(t, gmt, az, ft);
-            else lo = dbn_2pwl_next_step(t, gmt, az, ft, lo);
+            if (ff == 0 || ft < fprev) {
+                lo = dbn_2pwl_first_step(t, gmt, az, ft);
+                // age-table bracket of the step the walk resumes from (the walk only moves it up from here)
+                hint = bracket_increasing(n_interp, s_tevo[(lo < nsteps ? lo : nsteps - 1) + 1] + gmt + az, s_tage);
+            } else {
+                lo = dbn_2pwl_next_step_walk(t, gmt, az, ft, lo, hint);
+            }
             fprev = ft;
             s_lo[kk * F + ff] = (unsigned short)lo;
         }

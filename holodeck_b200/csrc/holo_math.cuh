@@ -283,6 +283,25 @@ HOLO_HD int dbn_2pwl_next_step(const Track2pwl& t, double gmt, double age_z, dou
     return lo;
 }
 
+// `fobs_right_of_step` for a walk over non-decreasing steps: the time at the right edge grows with the step, so the
+// bracket in the age table only ever moves up -- it is advanced from `hint` (<= the true bracket, e.g. the bracket of an
+// earlier step) instead of being bisected afresh.  Same index as `bracket_increasing`, hence the same value.
+HOLO_HD double fobs_right_of_step_walk(const Track2pwl& t, int s, double gmt, double age_z, int& hint) {
+    const double time_right = t.tevo[s + 1] + gmt + age_z;
+    int ir = hint;
+    const int last = t.n_interp - 2;
+    while (ir < last && t.tage[ir + 1] <= time_right) ++ir;
+    hint = ir;
+    double redz_right = interp_at_index(ir, time_right, t.tage, t.gz);
+    if (redz_right < 0.0) redz_right = 0.0;
+    return t.frst[s + 1] / (1.0 + redz_right);
+}
+
+HOLO_HD int dbn_2pwl_next_step_walk(const Track2pwl& t, double gmt, double age_z, double ftarget, int lo, int& hint) {
+    while (lo < t.nsteps && fobs_right_of_step_walk(t, lo, gmt, age_z, hint) < ftarget) ++lo;
+    return lo;
+}
+
 // Given `lo` = first step whose right edge reaches the target: returns true (and fills redz/dnum) iff some
 // integration step brackets `ftarget`; when several do (exact ties at step boundaries) the LAST one wins,
 // as in the reference's step-major loop order.
