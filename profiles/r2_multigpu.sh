@@ -7,6 +7,9 @@ OUT=gpurun_out/r2_multigpu
 mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 # (the driver records the weak-scaling curve itself at round end: SCALE_r02.json; here the STRONG-scaling line)
+for N in ${HOLO_WEAK_NS:-8}; do
+  $TR --nproc-per-node $N --master-port 2950$N bench.py --gpus $N --steps 10 --warmup 3 > $OUT/bench_weak_n$N.json 2> $OUT/bench_weak_n$N.err
+done
 for N in ${HOLO_STRONG_NS:-8}; do
   $TR --nproc-per-node $N --master-port 2951$N bench.py --gpus $N --steps 10 --warmup 3 --scaling strong --no-cpu-baseline > $OUT/bench_strong_n$N.json 2> $OUT/bench_strong_n$N.err
 done
@@ -15,7 +18,7 @@ rm -rf /tmp/lib1 /tmp/lib8 /tmp/lib8w1 /tmp/lib1ref
 python $GL /tmp/lib1ref -n 60 -r 100 -l 5 --gwb --ss --params --seed 1 --no-streaming > $OUT/genlib_1gpu_reference_fileplane.log 2>&1
 python $GL /tmp/lib1 -n 250 -r 100 -l 5 --gwb --ss --params --seed 1 > $OUT/genlib_1gpu.log 2>&1
 $TR --nproc-per-node 8 --master-port 29520 $GL /tmp/lib8 -n 2000 -r 100 -l 5 --gwb --ss --params --seed 1 > $OUT/genlib_8gpu.log 2>&1
-$TR --nproc-per-node 8 --master-port 29521 $GL /tmp/lib8w1 -n 2000 -r 100 -l 5 --gwb --ss --params --seed 1 --workers 2 --no-combine > $OUT/genlib_8gpu_2workers.log 2>&1
+$TR --nproc-per-node 8 --master-port 29521 $GL /tmp/lib8w1 -n 2000 -r 100 -l 5 --gwb --ss --params --seed 1 --no-pipeline --no-combine > $OUT/genlib_8gpu_nopipeline.log 2>&1
 ls -la /tmp/lib8 /tmp/lib8/library_store | head -20 >> $OUT/genlib_8gpu.log
 grep -h "library:\|combined\|rank 0" $OUT/genlib_*.log
 for f in $OUT/bench_*.json; do python - "$f" <<'PY'
