@@ -8,10 +8,11 @@ sample takes ~10 ms, so that file plane *is* the critical path (round 1: 615 -> 
 * the combined layout exists from the start: one ``.npy`` per dataset in ``<output>/library_store/`` with the
   reference's combined shapes -- ``gwb (S,F,R)``, ``hc_ss (S,F,R,L)``, ``hc_bg (S,F,R)``, ``sspar (S,4,F,R,L)``,
   ``bgpar (S,7,F,R)`` (``combine.py:140-175``) -- plus ``status (S,) uint8`` (0 = to do, 1 = done, 2 = failed:
-  what the existence / ``fail`` key of a per-sample file encodes in the reference) and ``fail_msg``.  Every rank
-  memory-maps the same files and writes only the rows of its own samples: no merge pass, no re-read;
+  what the existence / ``fail`` key of a per-sample file encodes in the reference) and ``failures.log``.  Every rank
+  opens the same files and writes only the rows of its own samples (one positioned write per row): no merge pass,
+  no re-read; readers (resume check, combine) memory-map them;
 * ``run_model`` leaves its products on the device; :class:`AsyncSampleWriter` copies them into a ring of PINNED
-  staging slots on a side stream and a background thread moves each finished slot into the memory maps, so neither
+  staging slots on a side stream and a background thread writes each finished slot into the store, so neither
   the device->host copy nor the file write sits between two samples;
 * ``combine.sam_lib_combine`` turns the store into the reference's single-file library when asked.
 """
@@ -52,6 +53,7 @@ class LibraryStore:
         self.maps = maps                  # name -> np.memmap (S, ...)
         self.status = maps["status"]
         self.fobs = None
+        self._fds = {}                    # name -> (file descriptor, byte offset of row 0, bytes per row): see `put`
 
     @classmethod
     def _dir(cls, output):
@@ -104,23 +106,46 @@ class LibraryStore:
     def is_done(self, pnum):
         return int(self.status[pnum]) == STATUS_DONE
 
+    def _row_file(self, name):
+        """(fd, offset of row 0, row bytes) of a dataset's ``.npy`` file, opened once per process."""
+        ent = self._fds.get(name)
+        if ent is None:
+            import os
+            mm = self.maps[name]
+            row = int(mm.dtype.itemsize * (np.prod(mm.shape[1:]) if mm.ndim > 1 else 1))
+            ent = (os.open(self.path.joinpath(f"{name}.npy"), os.O_RDWR), int(mm.offset), row)
+            self._fds[name] = ent
+        return ent
+
+    def _write_row(self, name, pnum, arr):
+        """One positioned write per row (``pwrite`` straight into the page cache).  Assigning into the shared memory
+        map instead takes a page fault per 4 KB page -- 270 per sample -- and with eight ranks mapping the same files
+        those faults serialise in the kernel (measured: 8-GPU library generation at 73 % of 8 x one GPU)."""
+        import os
+        fd, off, row = self._row_file(name)
+        buf = np.ascontiguousarray(arr, dtype=self.maps[name].dtype)
+        assert buf.nbytes == row, (name, buf.shape, self.maps[name].shape)
+        view = memoryview(buf).cast("B")
+        done = 0
+        while done < row:
+            done += os.pwrite(fd, view[done:], off + int(pnum) * row + done)
+
     def put(self, pnum, data):
         """Write the products of sample ``pnum`` (host arrays keyed like ``run_model``'s dict)."""
         for name in self.layout["datasets"]:
-            self.maps[name][pnum] = data[name]
-        self.status[pnum] = STATUS_DONE
+            self._write_row(name, pnum, data[name])
+        self._write_row("status", pnum, np.array([STATUS_DONE], dtype=np.uint8))
 
     def put_failure(self, pnum, message):
         """A failed sample: NaN rows, as ``combine.py:404-417`` produces from a ``fail`` file."""
         for name in self.layout["datasets"]:
-            self.maps[name][pnum] = np.nan
-        self.status[pnum] = STATUS_FAIL
+            self._write_row(name, pnum, np.full(self.maps[name].shape[1:], np.nan))
+        self._write_row("status", pnum, np.array([STATUS_FAIL], dtype=np.uint8))
         with open(self.path.joinpath("failures.log"), "a") as ff:
             ff.write(f"{int(pnum)}\t{message}\n")
 
     def flush(self):
-        for mm in self.maps.values():
-            mm.flush()
+        """Nothing to do: rows were written with `pwrite` (page cache; as durable as the reference's `np.savez`)."""
 
 
 class AsyncSampleWriter:
