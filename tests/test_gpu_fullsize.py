@@ -271,6 +271,55 @@ def test_fullsize_loudest_supplied_counts(holo, full):
     assert rel_err(cyutils.sam_poisson_gwb(number, h2fdf, 1, counts=cg), want_gwb) < 1e-12
 
 
+_REF_STATE = None
+
+
+def _ref_loudest_worker(job):
+    """one process of the reference's own sampler (numpy PCG64 inside the compiled Cython), seeded per process"""
+    from oracle import glue
+    seed, nreals, nloud = job
+    cy, _, _ = glue.ref()
+    cy.ORACLE_SEED = seed
+    st = _REF_STATE
+    ss, bg = cy.loudest_hc_from_sorted(st["number"], st["h2fdf"], nreals, nloud, st["msort"], st["qsort"], st["zsort"])
+    return np.asarray(ss), np.asarray(bg)
+
+
+def test_fullsize_realised_distribution_matches_reference_rng(holo, full):
+    """Statistical parity AT THE NAMED SIZE (north_star level 3): per-frequency 5 / 50 / 95 % quantiles of the
+    background, of the loudest source and of the total from the Philox/CUDA sampler (R = 2048) against the REFERENCE's
+    own RNG path -- `loudest_hc_from_sorted` of the compiled Cython drawing with numpy's PCG64 (cyutils.pyx:1266-1344),
+    one seeded process per host core, 256 realizations in all -- within bootstrap Monte-Carlo error."""
+    import multiprocessing as mp
+    import os
+    from holodeck_b200 import cyutils
+    global _REF_STATE
+    wl, st = full
+    _REF_STATE = st
+    L = 3
+    nproc = max(1, min(os.cpu_count() or 1, 32))
+    each = -(-256 // nproc)
+    with mp.get_context("fork").Pool(nproc) as pool:
+        parts = pool.map(_ref_loudest_worker, [(9000 + ii, each, L) for ii in range(nproc)], chunksize=1)
+    _REF_STATE = None
+    r_ss = np.concatenate([pp[0] for pp in parts], axis=1)
+    r_bg = np.concatenate([pp[1] for pp in parts], axis=1)
+    Rr = r_bg.shape[1]
+    g_ss, g_bg = cyutils.loudest_hc_from_sorted(st["number"], st["h2fdf"], 2048, L, st["msort"], st["qsort"], st["zsort"], seed=123)
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for name, ref, got in (("background", r_bg, g_bg), ("loudest", r_ss[..., 0], g_ss[..., 0]),
+                           ("total", r_bg + r_ss.sum(axis=-1), g_bg + g_ss.sum(axis=-1))):
+        ref, got = np.sqrt(ref), np.sqrt(got)                      # characteristic strain
+        qr, qg = np.percentile(ref, [5, 50, 95], axis=1), np.percentile(got, [5, 50, 95], axis=1)
+        boots = np.array([np.percentile(ref[:, rng.integers(0, Rr, Rr)], [5, 50, 95], axis=1) for _ in range(200)])
+        sig = boots.std(axis=0) * np.sqrt(1.0 + Rr / got.shape[1]) + 1e-3 * np.abs(qr)
+        dev = np.abs(qg - qr) / sig
+        worst = max(worst, float(dev.max()))
+        assert np.all(dev < 5.0), (name, float(dev.max()), np.unravel_index(np.argmax(dev), dev.shape))
+    print(f"fullsize realised quantiles vs reference RNG ({Rr} reference realizations on {nproc} cores): worst {worst:.2f} sigma")
+
+
 def test_fullsize_drop_in_boundary_through_aliased_modules(holo, full):
     """The boundary of SURVEY section 8(b), used the way INTEGRATION.md section 3 prescribes for a stock holodeck:
     the two compiled modules are replaced by `sys.modules` aliases, the caller imports them under the REFERENCE's
