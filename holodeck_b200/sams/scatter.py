@@ -77,22 +77,31 @@ def _dependency_levels(indptr, indices, npts):
     return order, level_ptr
 
 
-GS_THREADS, GS_LANES = 256, 8
-GS_SLOTS = GS_THREADS // GS_LANES
-#: one step of the Gauss-Seidel step program, byte for byte the `GsRec` of csrc/holo_scatter.cu
-_STEP_DTYPE = np.dtype([("e", "f8", (GS_THREADS, 4)), ("qinv", "f8", (GS_SLOTS, 4)), ("nb", "i4", GS_THREADS),
-                        ("vip", "i4", GS_SLOTS), ("hdr", "i4", 4)])
+GS_LANES = 8          # neighbours of one vertex handled per step
+GS_SLOTS = 32         # vertices of a level handled per step
+#: one step of the Gauss-Seidel step program, byte for byte the `GsRec` of csrc/holo_scatter.cu: what consumer thread
+#: ``t = 4 slot + sub`` needs lies at ``16 t`` of each plane (conflict-free 16-byte loads).  The thread owns edges
+#: ``sub`` (a) and ``sub + 4`` (b) of the vertex in ``slot``: planes ``e[0..3]`` = a's (2 ex, 2 ey), a's (ex, ey)/L^3,
+#: b's (2 ex, 2 ey), b's (ex, ey)/L^3; ``ids[t]`` = (a's neighbour, b's neighbour, the vertex or -1, step flags);
+#: ``qinv[0..1][slot]`` = the two rows of MINUS the inverse normal matrix.
+GS_THREADS = GS_SLOTS * (GS_LANES // 2)
+_STEP_DTYPE = np.dtype([("e", "f8", (4, GS_THREADS, 2)), ("qinv", "f8", (2, GS_SLOTS, 2)), ("ids", "i4", (GS_THREADS, 4))])
 
 
 def _step_program(indptr, indices, edge4, qinv, order, level_ptr):
     """Flatten the level schedule of the Gauss-Seidel sweep into fixed-size step records (geometry only).
 
-    A step handles up to ``GS_SLOTS`` vertices of ONE level (``GS_LANES`` lanes each, lane ``l`` taking neighbours
-    ``l, l + 8, ...`` in scipy's neighbour order -- the summation order of the round-1 kernel); vertices with more than
+    A step handles up to ``GS_SLOTS`` vertices of ONE level, ``GS_LANES`` neighbours each in scipy's neighbour order
+    (summed as the round-1 kernel did: neighbour ``l`` with ``l + 4``, then an xor-butterfly); vertices with more than
     8 neighbours (one hull corner of the named grid has 82) span several consecutive steps ("rounds"), the first
-    flagged to clear the sums, the last to apply the update.  The kernel streams these records with TMA bulk copies.
+    flagged (bit 0) to start the sums, the last (bit 1) to apply the update.  The kernel streams these records with
+    TMA bulk copies.  An absent edge points at the vertex itself with zero coefficients (it adds exactly nothing,
+    without a branch).  Two exact rescalings shorten the kernel's dependent fp64 chain: the record holds ``2 ex, 2 ey``
+    (the edge term is ``6 (f1 - f2) - 2 (-ex y0 - ey y1)``) and the NEGATED inverse normal matrix (the update stores
+    ``-(Q^-1 s)``).
     """
     deg = np.diff(indptr)
+    half = GS_LANES // 2
     steps = []
     for lv in range(level_ptr.size - 1):
         verts = order[level_ptr[lv]:level_ptr[lv + 1]]
@@ -101,19 +110,43 @@ def _step_program(indptr, indices, edge4, qinv, order, level_ptr):
             rounds = max(1, -(-int(deg[chunk].max()) // GS_LANES))
             for rr in range(rounds):
                 rec = np.zeros((), dtype=_STEP_DTYPE)
-                rec["nb"][:] = -1
-                rec["vip"][:] = -1
-                rec["vip"][:chunk.size] = chunk
-                rec["qinv"][:chunk.size] = qinv[chunk]
+                flags = (1 if rr == 0 else 0) | (2 if rr == rounds - 1 else 0)
+                ids = np.zeros((GS_SLOTS, half, 4), dtype=np.int32)              # (empty slots: vertex 0, e = 0)
+                ids[:, :, 2] = -1
+                ids[:, :, 3] = flags
+                ids[:chunk.size, :, 2] = chunk[:, None]
                 kk = rr * GS_LANES + np.arange(GS_LANES)[None, :]                 # (1, lanes) neighbour number
                 has = kk < deg[chunk][:, None]                                    # (slots, lanes)
                 jp = np.where(has, indptr[chunk][:, None] + kk, 0)
-                nb = np.where(has, indices[jp], -1)
-                rec["nb"][:chunk.size * GS_LANES] = nb.ravel()
-                rec["e"][:chunk.size * GS_LANES] = np.where(has[..., None], edge4[jp], 0.0).reshape(-1, 4)
-                rec["hdr"][0] = (1 if rr == 0 else 0) | (2 if rr == rounds - 1 else 0)
+                nb = np.where(has, indices[jp], chunk[:, None])                   # absent edge: the vertex itself, e = 0
+                ee = np.where(has[..., None], edge4[jp], 0.0)                     # (slots, lanes, 4)
+                ee[..., :2] *= 2.0                                                # the edge term uses 2 (e . y): exact
+                ids[:chunk.size, :, 0] = nb[:, :half]
+                ids[:chunk.size, :, 1] = nb[:, half:]
+                epl = np.zeros((4, GS_SLOTS, half, 2))
+                epl[0, :chunk.size] = ee[:, :half, 0:2]
+                epl[1, :chunk.size] = ee[:, :half, 2:4]
+                epl[2, :chunk.size] = ee[:, half:, 0:2]
+                epl[3, :chunk.size] = ee[:, half:, 2:4]
+                rec["e"] = epl.reshape(4, GS_THREADS, 2)
+                rec["ids"] = ids.reshape(GS_THREADS, 4)
+                qq = -qinv[chunk]                                                 # the update is y = -(Q^-1 s)
+                rec["qinv"][0, :chunk.size] = qq[:, 0:2]
+                rec["qinv"][1, :chunk.size] = qq[:, 2:4]
                 steps.append(rec)
     return np.array(steps, dtype=_STEP_DTYPE)
+
+
+def step_edges(rec):
+    """A step record back in per-vertex form: ``(vip (slots,), flags, nb (slots, 8), e (slots, 8, 4), qinv (slots, 4))``
+    (tests and the numpy emulation of the kernel)."""
+    half = GS_LANES // 2
+    ids = rec["ids"].reshape(GS_SLOTS, half, 4)
+    ee = rec["e"].reshape(4, GS_SLOTS, half, 2)
+    nb = np.concatenate([ids[:, :, 0], ids[:, :, 1]], axis=1)
+    e8 = np.concatenate([np.concatenate([ee[0], ee[1]], axis=-1), np.concatenate([ee[2], ee[3]], axis=-1)], axis=1)
+    qq = np.concatenate([rec["qinv"][0], rec["qinv"][1]], axis=-1)
+    return ids[:, 0, 2].copy(), int(ids[0, 0, 3]), nb, e8, qq
 
 
 def scatter_geometry(mtot, mrat, refine=4):
@@ -228,7 +261,7 @@ def _cached_geometry(mtot, mrat, refine):
         return scatter_geometry(mtot, mrat, refine)
     hh = hashlib.sha1()
     for part in (np.ascontiguousarray(mtot, dtype=np.float64).tobytes(), np.ascontiguousarray(mrat, dtype=np.float64).tobytes(),
-                 str(int(refine)).encode(), str(_STEP_DTYPE).encode(), str(_GEO_DTYPE).encode(), b"v3"):
+                 str(int(refine)).encode(), str(_STEP_DTYPE).encode(), str(_GEO_DTYPE).encode(), b"v6"):
         hh.update(part)
     fname = _cache_dir() / f"scatter_geometry_{hh.hexdigest()[:20]}.npz"
     try:

@@ -57,38 +57,33 @@ def test_geometry_and_restatement_against_scipy():
 
 
 def _run_step_program(prog, data, maxiter=400, tol=1e-6):
-    """numpy emulation of `ct_gradients_kernel` consuming the step program (8 lanes per vertex, butterfly sums)"""
-    from holodeck_b200.sams.scatter import GS_LANES, GS_SLOTS
+    """numpy emulation of `ct_gradients_kernel` consuming the step program (neighbour l summed with l + 4, then an
+    xor-butterfly over four lanes; doubled edge vectors and the negated inverse matrix, as the records hold them)"""
+    from holodeck_b200.sams.scatter import GS_LANES, GS_SLOTS, step_edges
     npts = data.size
     yy = np.zeros((npts, 2))
+    steps = [step_edges(rec) for rec in prog]
     for it in range(maxiter):
         err = 0.0
-        acc = np.zeros((GS_SLOTS * GS_LANES, 2))
-        for rec in prog:
-            flags = int(rec["hdr"][0])
-            if flags & 1:
-                acc[:] = 0.0
-            nb = rec["nb"]
-            on = nb >= 0
-            ip = np.repeat(rec["vip"], GS_LANES)
-            ee = rec["e"]
-            df2 = -ee[on, 0] * yy[nb[on], 0] - ee[on, 1] * yy[nb[on], 1]
-            num = 6 * (data[ip[on]] - data[nb[on]]) - 2 * df2
-            acc[on, 0] += num * ee[on, 2]
-            acc[on, 1] += num * ee[on, 3]
+        acc = np.zeros((GS_SLOTS, GS_LANES, 2))
+        for vip, flags, nb, ee, qq in steps:
+            vv = np.maximum(vip, 0)[:, None]
+            df2x2 = -ee[..., 0] * yy[nb, 0] - ee[..., 1] * yy[nb, 1]
+            num = 6 * (data[vv] - data[nb]) - df2x2
+            pp = np.stack([num * ee[..., 2], num * ee[..., 3]], axis=-1)
+            acc = pp if flags & 1 else acc + pp
             if flags & 2:
-                tt = acc.reshape(GS_SLOTS, GS_LANES, 2).copy()
+                tt = acc.copy()
                 for off in (4, 2, 1):                                   # xor butterfly, as the shuffles
                     tt = tt + tt[:, np.arange(GS_LANES) ^ off, :]
                 tot = tt[:, 0, :]
-                for jj, vv in enumerate(rec["vip"]):
-                    if vv < 0:
+                for jj, vx in enumerate(vip):
+                    if vx < 0:
                         continue
-                    qq = rec["qinv"][jj]
-                    r0 = qq[0] * tot[jj, 0] + qq[1] * tot[jj, 1]
-                    r1 = qq[2] * tot[jj, 0] + qq[3] * tot[jj, 1]
-                    change = max(abs(yy[vv, 0] + r0), abs(yy[vv, 1] + r1))
-                    yy[vv] = (-r0, -r1)
+                    r0 = qq[jj, 0] * tot[jj, 0] + qq[jj, 1] * tot[jj, 1]
+                    r1 = qq[jj, 2] * tot[jj, 0] + qq[jj, 3] * tot[jj, 1]
+                    change = max(abs(yy[vx, 0] - r0), abs(yy[vx, 1] - r1))
+                    yy[vx] = (r0, r1)
                     err = max(err, change / max(1.0, abs(r0), abs(r1)))
         if err < tol:
             return yy, it + 1
@@ -106,12 +101,15 @@ def test_step_program_reproduces_the_sequential_sweep():
         geo = scatter.scatter_geometry(mtot, mrat, refine=4)
         prog = geo["program"]
         deg = np.diff(geo["indptr"])
-        assert prog.dtype.itemsize == 10384 and prog["hdr"][0, 0] & 1 and prog["hdr"][-1, 0] & 2
+        assert prog.dtype.itemsize == 11264 and prog["ids"][0, 0, 3] & 1 and prog["ids"][-1, 0, 3] & 2
         # every directed edge appears exactly once, under its own vertex
         pairs = set()
         for rec in prog:
-            ip = np.repeat(rec["vip"], scatter.GS_LANES)
-            for aa, bb in zip(ip[rec["nb"] >= 0], rec["nb"][rec["nb"] >= 0]):
+            vip, flags, nb, ee, qq = scatter.step_edges(rec)
+            ip = np.repeat(vip[:, None], scatter.GS_LANES, axis=1)
+            real = (ip >= 0) & (nb != ip)
+            assert not ee[~real].any()                                     # absent edges carry zero coefficients
+            for aa, bb in zip(ip[real], nb[real]):
                 assert (int(aa), int(bb)) not in pairs
                 pairs.add((int(aa), int(bb)))
         assert len(pairs) == geo["indices"].size
