@@ -412,13 +412,21 @@ struct CtPoint {       // geometry of one regular-grid point (host-computed)
     double g[3];       // affine-invariant edge parameters (neighbour centroids)
 };
 
-__global__ void __launch_bounds__(128)
+// Flat over (point, z), z fastest: consecutive threads write consecutive doubles, no lane idles on Z = 101, and the 88 %
+// of the regular grid that lies outside the hull (nearest fill) reads 8 bytes of its point's geometry, not the record.
+__global__ void __launch_bounds__(256)
 ct_eval_kernel(int64_t ngrid, int Z, const CtPoint* __restrict__ geo, const double* __restrict__ data /* (npts, Z) */,
                const double* __restrict__ grad /* (npts, 2, Z) */, double* __restrict__ out /* (ngrid, Z) */,
                int* __restrict__ flags /* [0]: a bad value survived the nearest fill */) {
-    const int64_t p = blockIdx.x;
-    const CtPoint gp = geo[p];
-    for (int z = threadIdx.x; z < Z; z += blockDim.x) {
+    const uint32_t total = (uint32_t)(ngrid * Z), stride = gridDim.x * blockDim.x;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const uint32_t p = idx / (uint32_t)Z;
+        const int z = (int)(idx - p * (uint32_t)Z);
+        const int2 head = *reinterpret_cast<const int2*>(&geo[p]);      // simplex, nearest
+        CtPoint gp;
+        gp.simplex = head.x;
+        gp.nearest = head.y;
+        if (gp.simplex >= 0) gp = geo[p];
         double w = nan("");
         if (gp.simplex >= 0) {
             const double f1 = data[(int64_t)gp.v[0] * Z + z], f2 = data[(int64_t)gp.v[1] * Z + z],
@@ -469,7 +477,7 @@ ct_eval_kernel(int64_t ngrid, int Z, const CtPoint* __restrict__ geo, const doub
             w = data[(int64_t)gp.nearest * Z + z];
             if (isnan(w) || w < 0.0) atomicOr(&flags[0], 1);              // sam.py:1376-1380 raises
         }
-        out[p * Z + z] = w;
+        out[idx] = w;
     }
 }
 
@@ -523,9 +531,11 @@ int holo_scatter_gradients(int npts, int Z, const void* program, int nsteps, con
 int holo_scatter_ct_eval(int64_t ngrid, int Z, const void* geo, const double* data, const double* grad, double* out,
                          int* flags, void* stream) {
     HOLO_REQUIRE(geo && data && grad && out && flags, "holo_scatter_ct_eval: NULL argument");
-    HOLO_REQUIRE(ngrid > 0 && ngrid < 2147483647LL && Z > 0, "holo_scatter_ct_eval: bad shape");
+    HOLO_REQUIRE(ngrid > 0 && Z > 0 && ngrid * Z < 4294967295LL, "holo_scatter_ct_eval: bad shape");
     HOLO_CUDA(cudaMemsetAsync(flags, 0, sizeof(int), (cudaStream_t)stream));
-    ct_eval_kernel<<<(int)ngrid, 128, 0, (cudaStream_t)stream>>>(ngrid, Z, (const CtPoint*)geo, data, grad, out, flags);
+    const int64_t want = (ngrid * Z + 255) / 256;
+    const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);        // a few resident waves, grid-stride
+    ct_eval_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ngrid, Z, (const CtPoint*)geo, data, grad, out, flags);
     holo::count_launches(1);
     return holo_check_launch("holo_scatter_ct_eval");
 }
