@@ -285,6 +285,29 @@ def _cached_geometry(mtot, mrat, refine):
     return gg
 
 
+def _gemm_blocks(i0, i1, G, nblk=4):
+    """Row / column blocks of the scattered regular grid that the back-interpolation reads.
+
+    `RegularGridInterpolator` touches the four corners ``(i0 + {0,1}, i1 + {0,1})`` of each data point only, and in
+    (log m1, log m2) the data points fill the band ``1e-3 m1 <= m2 <= m1``: about a tenth of the ``G x G`` grid (10.6 % at
+    the named grid).  The scatter product is therefore evaluated per block of secondary-mass columns, for the contiguous
+    range of primary-mass rows that block needs.  Measured on B200 at the named grid (device time): the full product
+    0.34 ms; 4 blocks (24 % of the flops) 0.118 ms, 8 blocks (18 %) 0.142 ms, 16 blocks (15 %) 0.183 ms -- the small
+    products are launch- and tile-bound, so few blocks win; the values are bit-identical to the full product's."""
+    need = np.zeros((G, G), dtype=bool)
+    for da in (0, 1):
+        for db in (0, 1):
+            need[np.minimum(i0 + da, G - 1), np.minimum(i1 + db, G - 1)] = True
+    cols = np.flatnonzero(need.any(axis=0))
+    edges = np.unique(np.linspace(cols.min(), cols.max() + 1, nblk + 1).astype(int))
+    blocks = []
+    for b0, b1 in zip(edges[:-1], edges[1:]):
+        rows = np.flatnonzero(need[:, b0:b1].any(axis=1))
+        if rows.size:
+            blocks.append((int(rows.min()), int(rows.max()) + 1, int(b0), int(b1)))
+    return blocks
+
+
 def _device_geometry(mtot, mrat, refine):
     import torch
     key = (np.asarray(mtot).tobytes(), np.asarray(mrat).tobytes(), int(refine), torch.cuda.current_device())
@@ -299,6 +322,7 @@ def _device_geometry(mtot, mrat, refine):
             dev[name] = _lib.to_dev(gg[name], dtype=torch.int32)
         for name in ("y0", "y1"):
             dev[name] = _lib.to_dev(gg[name])
+        dev["gemm_blocks"] = _gemm_blocks(np.asarray(gg["i0"]), np.asarray(gg["i1"]), int(gg["G"]))
         dev["geo"] = torch.from_numpy(gg["geo"].view(np.uint8).copy()).to(_lib.device())
         dev["program"] = torch.from_numpy(gg["program"].view(np.uint8).copy()).to(_lib.device())
         if len(_GEO_CACHE) > 8:
@@ -356,7 +380,13 @@ def add_scatter_to_masses(mtot, mrat, dens, scatter, refine=4, log=None, *, _def
     rc = lib.holo_scatter_ct_eval(G * G, Z, _lib.ptr(gg["geo"]), _lib.ptr(data), _lib.ptr(grad), _lib.ptr(grid),
                                   _lib.ptr(flags), _lib.stream())
     _lib.check(rc, "add_scatter_to_masses (interpolation)")
-    grid = torch.matmul(w2t, grid.reshape(G, G * Z))          # (G, G*Z): cuBLAS DGEMM, new[k, ...] = sum_j (WW)[j, k] A[j, ...]
+    # cuBLAS DGEMMs, new[k, b, z] = sum_j (WW)[j, k] A[j, b, z], for the blocks the back-interpolation reads only
+    # (the rest of `scat` stays unwritten and is never read)
+    a2 = grid.reshape(G, G * Z)
+    scat = _lib.empty((G, G * Z))
+    for k0, k1, b0, b1 in gg["gemm_blocks"]:
+        torch.mm(w2t[k0:k1], a2[:, b0 * Z:b1 * Z], out=scat[k0:k1, b0 * Z:b1 * Z])
+    grid = scat
     out = _lib.empty((npts, Z))
     rc = lib.holo_scatter_bilinear(npts, G, Z, _lib.ptr(gg["i0"]), _lib.ptr(gg["i1"]), _lib.ptr(gg["y0"]), _lib.ptr(gg["y1"]),
                                    _lib.ptr(grid), _lib.ptr(out), _lib.stream())

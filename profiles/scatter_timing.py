@@ -37,7 +37,24 @@ t, _ = tm(lambda: lib.holo_scatter_ct_eval(G*G, Z, _lib.ptr(gg["geo"]), _lib.ptr
 print("K6b CT eval + fill: %.2f ms" % t)
 w2t = gg[("weights", 0.3)]
 t, g2 = tm(lambda: torch.matmul(w2t, grid.reshape(G, G*Z)))
-print("DGEMM (%d x %d) x (%d x %d): %.2f ms = %.1f TFLOP/s" % (G, G, G, G*Z, t, 2*G*G*G*Z/t/1e9))
+print("full DGEMM (%d x %d) x (%d x %d): %.2f ms = %.1f TFLOP/s" % (G, G, G, G*Z, t, 2*G*G*G*Z/t/1e9))
+for nblk in (2, 3, 4, 6, 8, 16):
+    blocks = scatter._gemm_blocks(gg["i0"].cpu().numpy(), gg["i1"].cpu().numpy(), G, nblk)
+    a2 = grid.reshape(G, G*Z); sc = _lib.empty((G, G*Z))
+    def blocked():
+        for k0, k1, b0, b1 in blocks:
+            torch.mm(w2t[k0:k1], a2[:, b0*Z:b1*Z], out=sc[k0:k1, b0*Z:b1*Z])
+        return sc
+    t, g3 = tm(blocked)
+    # device-only time: queue the calls behind a long kernel so that the host is never the bottleneck
+    big = torch.empty((8192, 8192), device="cuda"); tq = []
+    for rep in range(3):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        torch.mm(big, big); e0.record(); blocked(); e1.record(); torch.cuda.synchronize(); tq.append(e0.elapsed_time(e1))
+    tdev = min(tq)
+    fl = sum(2.0*(k1-k0)*G*(b1-b0)*Z for k0, k1, b0, b1 in blocks)
+    err = max(float((g3[k0:k1, b0*Z:b1*Z] - g2[k0:k1, b0*Z:b1*Z]).abs().max()) for k0, k1, b0, b1 in blocks)
+    print("blocked DGEMM, %2d column blocks: %.3f ms launched live, %.3f ms of device time (%.0f %% of the flops, %.1f TFLOP/s), max |diff| to the full product %.1e" % (len(blocks), t, tdev, 100*fl/(2.0*G*G*G*Z), fl/tdev/1e9, err))
 outp = _lib.empty((npts, Z))
 t, _ = tm(lambda: lib.holo_scatter_bilinear(npts, G, Z, _lib.ptr(gg["i0"]), _lib.ptr(gg["i1"]), _lib.ptr(gg["y0"]), _lib.ptr(gg["y1"]), _lib.ptr(g2), _lib.ptr(outp), _lib.stream()))
 print("K6c bilinear: %.2f ms" % t)
