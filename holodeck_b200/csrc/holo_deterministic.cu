@@ -182,6 +182,8 @@ dbn_2pwl_kernel(CyConsts cc, const double* __restrict__ fobs, int F, double sepa
         s_gdc[i] = grid_dcom[i];
     }
     for (int i = tid; i < F; i += DBN_THREADS) s_fobs[i] = fobs[i];
+    __shared__ MqConsts s_mqc;
+    if (tid == 32) s_mqc = mq_consts(cc, mt, mr);                        // (three pow calls: once per CTA, not per thread)
     if (tid == 0) {
         double risco = 3.0 * CY_SCHW * mt;                               // pyx:609
         double dx = (sepa_init_log10 - log10(risco)) / nsteps;          // pyx:610
@@ -224,7 +226,7 @@ dbn_2pwl_kernel(CyConsts cc, const double* __restrict__ fobs, int F, double sepa
     t.tage = s_tage; t.gz = s_gz; t.gdc = s_gdc; t.n_interp = n_interp;
     t.age_universe = s_tage[n_interp - 1];                               // pyx:579
 
-    const MqConsts mqc = mq_consts(cc, mt, mr);
+    const MqConsts mqc = s_mqc;
     int64_t base = (int64_t)mq * Z;
     int nzf = Z * F;
     // phase 2: one thread per redshift finds, for every target frequency, the first step whose right edge reaches
@@ -233,16 +235,17 @@ dbn_2pwl_kernel(CyConsts cc, const double* __restrict__ fobs, int F, double sepa
     unsigned short* s_lo = reinterpret_cast<unsigned short*>(s_fobs + F);   // (Z, F)
     for (int kk = tid; kk < Z; kk += DBN_THREADS) {
         const double gmt = gmt_time[base + kk], az = s_zage[kk];
-        int lo = 0, hint = 0;
-        double fprev = 0.0;
+        int lo = 0, hint = 0, fr_lo = -1;
+        double fprev = 0.0, fr = 0.0;
         for (int ff = 0; ff < F; ++ff) {
             const double ft = s_fobs[ff];
             if (ff == 0 || ft < fprev) {
                 lo = dbn_2pwl_first_step(t, gmt, az, ft);
                 // age-table bracket of the step the walk resumes from (the walk only moves it up from here)
                 hint = bracket_increasing(n_interp, s_tevo[(lo < nsteps ? lo : nsteps - 1) + 1] + gmt + az, s_tage);
+                fr_lo = -1;
             } else {
-                lo = dbn_2pwl_next_step_walk(t, gmt, az, ft, lo, hint);
+                lo = dbn_2pwl_next_step_walk(t, gmt, az, ft, lo, hint, fr_lo, fr);
             }
             fprev = ft;
             s_lo[kk * F + ff] = (unsigned short)lo;

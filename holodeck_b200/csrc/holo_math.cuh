@@ -297,8 +297,18 @@ HOLO_HD double fobs_right_of_step_walk(const Track2pwl& t, int s, double gmt, do
     return t.frst[s + 1] / (1.0 + redz_right);
 }
 
-HOLO_HD int dbn_2pwl_next_step_walk(const Track2pwl& t, double gmt, double age_z, double ftarget, int lo, int& hint) {
-    while (lo < t.nsteps && fobs_right_of_step_walk(t, lo, gmt, age_z, hint) < ftarget) ++lo;
+// (`fr_lo` / `fr` remember the right-edge frequency of the step the previous target stopped at: several target
+//  frequencies usually fall into the same step, and the walk would evaluate that step again for each of them)
+HOLO_HD int dbn_2pwl_next_step_walk(const Track2pwl& t, double gmt, double age_z, double ftarget, int lo, int& hint,
+                                    int& fr_lo, double& fr) {
+    while (lo < t.nsteps) {
+        if (fr_lo != lo) {
+            fr = fobs_right_of_step_walk(t, lo, gmt, age_z, hint);
+            fr_lo = lo;
+        }
+        if (!(fr < ftarget)) break;
+        ++lo;
+    }
     return lo;
 }
 
