@@ -339,7 +339,7 @@ int holo_model_details_hist(const double* redz_edges /* (Z,) */, const double* r
  *      CloughTocher2DInterpolator + NearestNDInterpolator fill -> two dense scatter products ->
  *      RegularGridInterpolator(linear).  The geometry (Delaunay triangulation of the (log10 m1, log10 m2)
  *      images of the grid, point location, level schedule of the Gauss-Seidel sweep) is data-independent and
- *      prepared once per grid by the host driver (holodeck_b200/sams/scatter.py); the two products are plain
+ *      prepared once per grid by the host driver (holodeck_b200/sams/scatter.py); the scatter products are plain
  *      DGEMMs (cuBLAS) between `holo_scatter_ct_eval` and `holo_scatter_bilinear`.
  *      Layouts: density (npts = M*Q, Z) z fastest; gradients (npts, 2, Z); regular grid (G, G, Z).
  * ------------------------------------------------------------------------------------------- */
@@ -347,11 +347,17 @@ int holo_model_details_hist(const double* redz_edges /* (Z,) */, const double* r
 /* gradients at the triangulation vertices: scipy interpnd `_estimate_gradients_2d_global` (Gauss-Seidel,
  * maxiter / tol as CloughTocher2DInterpolator: 400, 1e-6), all Z slices at once.
  * `program` (16-byte aligned, nsteps records of holo_scatter_step_bytes() bytes): the level schedule of the sweep
- * flattened by the host into one fixed-size record per step -- per thread (8 lanes per vertex, 32 vertices per step)
- * the neighbour vertex and ex, ey, ex/L^3, ey/L^3 of the edge (Delaunay.vertex_neighbor_vertices order), per vertex
- * slot the vertex and the inverse of its 2x2 normal matrix, and a header word (bit 0: first round of the step's
- * vertices, bit 1: last round).  The kernel streams the records through shared memory with TMA bulk copies
- * (cp.async.bulk + mbarrier).  niter (Z,) (may be NULL): sweeps used, 0 = not converged. */
+ * flattened by the host into one fixed-size, plane-ordered record per step (32 vertices of one level, 8 neighbours
+ * each in Delaunay.vertex_neighbor_vertices order; 128 consumer threads t = 4 slot + sub, each owning neighbours `sub`
+ * and `sub + 4` of the vertex in `slot`):
+ *     double e[4][128][2]   a: (2 ex, 2 ey) | a: (ex, ey)/L^3 | b: (2 ex, 2 ey) | b: (ex, ey)/L^3
+ *     double qinv[2][32][2] the two rows of MINUS the inverse of the vertex's 2x2 normal matrix
+ *     int    ids[128][4]    a's neighbour, b's neighbour, the vertex (-1: empty slot), flags (bit 0: first round of the
+ *                           step's vertices, bit 1: last round -> apply the update)
+ * An absent edge points at the vertex itself (vertex 0 in an empty slot) with zero coefficients.  The kernel streams the
+ * records through shared memory with TMA bulk copies (cp.async.bulk + mbarrier) issued by a producer warp.
+ * niter (Z,) (may be NULL): sweeps used, 0 = not converged.  The regular-grid values the back-interpolation does not
+ * read need not be computed: the host driver evaluates the scatter product for the needed row/column blocks only. */
 int holo_scatter_step_bytes(void);
 int holo_scatter_gradients(int npts, int Z, const void* program, int nsteps, const double* data, int maxiter,
                            double tol, double* grad, int* niter, void* stream);
