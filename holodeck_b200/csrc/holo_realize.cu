@@ -22,6 +22,8 @@
 //     be too short the call reports HOLO_ERR_OVERFLOW and the host retries with a larger margin.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "holo_api.cuh"
 #include <string.h>
 
@@ -1818,7 +1820,14 @@ static Plan make_plan(int64_t ncell, int F, int R, int variant) {
     // 1024 chunks: the heaviest (chunk, frequency group) item bounds the kernel from below -- 9.2 ms of a 10.3 ms
     // launch with 512 chunks at R = 1000, and MORE than the balanced time at R = 100 (4.2 vs 3.2 ms).  1024 halves
     // it (R = 100: 4.3 -> 3.5 ms); 2048 gains nothing more and costs partial-sum traffic at R = 1000.
-    int64_t nchunk = 1024;
+    // The quad kernels take ONE frequency per item: the same number of items (and the same work per item) needs a
+    // quarter of the chunks, and their 11-accumulator partial sums -- nchunk*F*11*R*8 bytes, 3.6 GB at R = 1000 with
+    // 1024 chunks -- shrink with it.  Measured (loud+par L=5, R = 1000 / R = 100, ms): 1024 chunks 16.84 / 5.97,
+    // 512: 16.12 / 5.91, 256: 15.75 / 5.92, 128: 15.90 / 6.18  (-DHOLO_QUAD_NCHUNK=... for sweeps).
+#ifndef HOLO_QUAD_NCHUNK
+#define HOLO_QUAD_NCHUNK 256
+#endif
+    int64_t nchunk = uses_quad_kernel(variant) ? HOLO_QUAD_NCHUNK : 1024;
     int64_t chunk = (ncell + nchunk - 1) / nchunk;
     chunk = ((chunk + 63) / 64) * 64;
     if (chunk < 64) chunk = 64;

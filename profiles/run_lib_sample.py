@@ -7,7 +7,7 @@ import bench
 from holodeck_b200 import librarian
 args = argparse.Namespace(shape=[91, 81, 101], nfreqs=40, realize=100, loudest=5)
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 1):
-    sam, hard = bench.make_models(args)
+    sam, hard = bench.make_models(args, scatter_dex=float(sys.argv[2]) if len(sys.argv) > 2 else 0.3)
     out = librarian.run_model(sam, hard, nreals=100, nloudest=5, params_flag=True, seed=1)
 torch.cuda.synchronize()
 print("done", sorted(out.keys()))
