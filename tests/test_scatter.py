@@ -123,6 +123,29 @@ def test_step_program_reproduces_the_sequential_sweep():
             assert np.abs(g_prog - g_seq).max() <= 1e-12 * (np.abs(g_seq).max() + 1e-300)
 
 
+def test_scatter_product_blocks_cover_what_the_back_interpolation_reads():
+    """`_gemm_blocks`: the row/column blocks for which the scatter product is evaluated contain every corner the
+    bilinear back-interpolation touches (anything else of the scattered grid stays unwritten), for any block count."""
+    from holodeck_b200.sams import scatter
+    for (M, Q) in ((14, 11), (40, 37)):
+        mtot, mrat, _ = small_case(M, Q, 2, 0)
+        geo = scatter.scatter_geometry(mtot, mrat, refine=4)
+        G, i0, i1 = geo["G"], np.asarray(geo["i0"]), np.asarray(geo["i1"])
+        assert i0.max() <= G - 2 and i1.max() <= G - 2 and i0.min() >= 0 and i1.min() >= 0
+        for nblk in (1, 3, 4, 9):
+            blocks = scatter._gemm_blocks(i0, i1, G, nblk)
+            cover = np.zeros((G, G), dtype=bool)
+            for k0, k1, b0, b1 in blocks:
+                assert 0 <= k0 < k1 <= G and 0 <= b0 < b1 <= G
+                assert not cover[:, b0:b1].any()                       # column blocks do not overlap
+                cover[k0:k1, b0:b1] = True
+            for da in (0, 1):
+                for db in (0, 1):
+                    assert cover[i0 + da, i1 + db].all()
+        # the point of the exercise: the needed region is a small part of the grid
+        assert cover.mean() < 0.6
+
+
 def test_port_pipeline_matches_reference_procedure():
     import scipy.stats
     from holodeck_b200.sams import scatter
