@@ -160,6 +160,39 @@ def test_port_pipeline_matches_reference_procedure():
 
 
 @pytest.mark.gpu
+def test_gradients_kernel_against_the_step_program_emulation_at_sweep_limits():
+    """`ct_gradients_kernel` alone, with the sweep limit set to 1, 2, 3 and 400 on grids with odd and even step counts:
+    gradients and sweep counts must follow the numpy execution of the same step program.  This pins the kernel's ring
+    protocol where it is most delicate -- the speculative fetch of the next sweep's first record, the producer warp's stop
+    at convergence or at the limit, the register sets swapping roles on an odd step count -- and the `niter = 0` (not
+    converged) report."""
+    import torch
+    from holodeck_b200 import _lib
+    from holodeck_b200.sams import scatter
+    lib = _lib.require_gpu()
+    seen = set()
+    for (M, Q, Z, seed) in ((14, 11, 4, 0), (15, 11, 3, 1), (23, 17, 2, 2)):
+        mtot, mrat, dens = small_case(M, Q, Z, seed)
+        geo = scatter.scatter_geometry(mtot, mrat, refine=4)
+        dev = scatter._device_geometry(mtot, mrat, 4)
+        npts = geo["npts"]
+        seen.add(int(geo["program"].size) % 2)
+        data = _lib.to_dev(dens).reshape(npts, Z)
+        for maxiter in (1, 2, 3, 400):
+            grad = _lib.empty((npts, 2, Z))
+            niter = torch.full((Z,), -7, dtype=torch.int32, device=data.device)
+            rc = lib.holo_scatter_gradients(npts, Z, _lib.ptr(dev["program"]), dev["nsteps"], _lib.ptr(data), maxiter, 1e-6,
+                                            _lib.ptr(grad), _lib.ptr(niter), _lib.stream())
+            _lib.check(rc, "gradients")
+            got, gn = _lib.to_host(grad), niter.cpu().numpy()
+            for zz in range(Z):
+                want, wn = _run_step_program(geo["program"], dens.reshape(npts, Z)[:, zz], maxiter=maxiter)
+                assert gn[zz] == wn, (M, Q, zz, maxiter, gn[zz], wn)
+                assert np.abs(got[:, :, zz] - want).max() <= 1e-12 * (np.abs(want).max() + 1e-300)
+    assert seen == {0, 1}, "both parities of the step count must be exercised"
+
+
+@pytest.mark.gpu
 def test_device_scatter_matches_reference_procedure():
     from holodeck_b200.sams import scatter
     from oracle import glue
